@@ -1,0 +1,135 @@
+/*
+ * wlk_b200.h -- C ABI of the B200-native streaming-Whisper engine.
+ *
+ * The reference (QuentinFuxa/WhisperLiveKit) has no FFI: its plugin surface for
+ * this path is Python duck-typing.  This header is the boundary a
+ * maintainer would bind (ctypes) underneath those seams; each
+ * entry point names the reference interface it replaces.  Conventions:
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from wlk_last_error() (thread-local);
+ *   - no exceptions, no C++/torch types cross the boundary: plain pointers+sizes;
+ *   - "host" pointers are caller-owned host memory, "dev" pointers device memory
+ *     on the engine's device; the engine owns all device state it allocates;
+ *   - calls on one engine are serialised internally (one mutex, one CUDA stream);
+ *     concurrency comes from batching sessions into one call.
+ */
+#ifndef WLK_B200_H
+#define WLK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WLK_ABI_VERSION 1
+
+typedef struct wlk_engine wlk_engine;
+
+/* ModelDimensions, reference whisperlivekit/whisper/model.py:25-36 */
+typedef struct wlk_dims {
+    int32_t n_mels, n_audio_ctx, n_audio_state, n_audio_head, n_audio_layer;
+    int32_t n_vocab, n_text_ctx, n_text_state, n_text_head, n_text_layer;
+} wlk_dims;
+
+enum { WLK_PREC_FP32 = 0,   /* SIMT fp32 kernels end to end: the 1e-3-on-logits parity mode      */
+       WLK_PREC_BF16 = 1 }; /* bf16 operands / fp32 accumulate + fp32 residual: the serving mode  */
+enum { WLK_BACKEND_AUTO = 0, WLK_BACKEND_SIMT = 1, WLK_BACKEND_TCGEN05 = 2 };
+
+typedef struct wlk_config {
+    int32_t device;          /* CUDA ordinal */
+    int32_t precision;       /* WLK_PREC_* */
+    int32_t max_sessions;    /* device state is pooled for this many sessions */
+    int32_t max_batch;       /* sessions per encode/decode call */
+    int32_t gemm_backend;    /* WLK_BACKEND_* (AUTO: tcgen05 in bf16 mode, SIMT in fp32 mode) */
+    int32_t attn_backend;    /* WLK_BACKEND_* for the encoder self-attention */
+    int32_t max_align_heads; /* capacity of the alignment-head export */
+    int32_t reserved;
+} wlk_config;
+
+const char* wlk_last_error(void);
+int wlk_abi_version(void);
+
+/* ---- engine lifetime + weights: replaces whisper.load_model()/Whisper.__init__
+ *      (reference whisperlivekit/whisper/__init__.py:466-596, model.py:335-361)            */
+int wlk_engine_create(const wlk_dims* dims, const wlk_config* cfg, wlk_engine** out);
+int wlk_engine_destroy(wlk_engine* e);
+/* name = reference state_dict key ("encoder.blocks.0.attn.query.weight", ...), plus
+ * "mel_filters" [n_mels,201] and "hann_window" [400]; data = host fp32, row-major.        */
+int wlk_engine_load_tensor(wlk_engine* e, const char* name, const float* host, const int64_t* shape, int ndim);
+int wlk_engine_finalize_weights(wlk_engine* e);
+/* packed device weight blob (for an NCCL broadcast done by the host at init)             */
+int wlk_engine_weight_blob(wlk_engine* e, void** dev, size_t* nbytes);
+int wlk_engine_adopt_weights(wlk_engine* e);   /* after the blob was filled by a broadcast */
+/* (layer, head) pairs, reference model.alignment_heads (model.py:357-370) iteration order */
+int wlk_engine_set_alignment_heads(wlk_engine* e, const int32_t* layer_head_pairs, int n_pairs);
+int wlk_engine_stream(wlk_engine* e, void** cuda_stream);
+int wlk_engine_sync(wlk_engine* e);
+int wlk_engine_memory(wlk_engine* e, size_t* weights, size_t* sessions, size_t* workspace);
+
+/* ---- per-session state: replaces DecoderState + AlignAtt.insert_audio
+ *      (reference simul_whisper/decoder_state.py:7-91, simul_whisper.py:219-237)           */
+int wlk_session_open(wlk_engine* e, int32_t* sid);
+int wlk_session_close(wlk_engine* e, int32_t sid);
+int wlk_session_append_audio(wlk_engine* e, int32_t sid, const float* pcm_host, int64_t n);
+int wlk_session_drop_audio(wlk_engine* e, int32_t sid, int64_t n_front_samples);
+int wlk_session_clear_audio(wlk_engine* e, int32_t sid);
+int wlk_session_audio_len(wlk_engine* e, int32_t sid, int64_t* n);
+
+/* ---- hot path, batched over sessions -------------------------------------------------
+ * wlk_encode: AlignAtt._encode (simul_whisper.py:299-352) = log_mel_spectrogram
+ *   (whisper/audio.py:110-157) + AudioEncoder.forward (model.py:238-254), plus the cross-
+ *   attention K/V projection the reference does lazily (model.py:116-125).  Starts a new
+ *   inference epoch for the session (the reference drops its KV cache after every infer,
+ *   align_att_base.py:312).  content_mel_len_out[i] as simul_whisper.py:350.              */
+int wlk_encode(wlk_engine* e, const int32_t* sids, int n, int32_t* content_mel_len_out);
+/* wlk_decode: AlignAtt._get_logits_and_cross_attn (simul_whisper.py:357-368) =
+ *   TextDecoder.forward with kv_cache + return_cross_attn (model.py:281-332).  Feeds
+ *   tokens[offsets[i]..offsets[i+1]) to session i at its current self-KV offset.  Keeps
+ *   the last-row logits (and, on the first call of an epoch, the row at sot_index) and
+ *   the alignment heads' softmaxed cross-attention rows on the device.                    */
+int wlk_decode(wlk_engine* e, const int32_t* sids, int n, const int32_t* tokens, const int32_t* offsets,
+               int32_t sot_index);
+/* AlignAtt._check_no_speech (simul_whisper.py:370-377)                                     */
+int wlk_no_speech_prob(wlk_engine* e, const int32_t* sids, int n, float* prob_out);
+/* _suppress_blank_tokens / SuppressTokens.apply (simul_whisper.py:379-385, decoding.py:427) */
+int wlk_suppress(wlk_engine* e, const int32_t* sids, int n, const int32_t* token_ids, int n_tokens);
+/* logits[tok] += bias: device half of _apply_dry_penalty (align_att_base.py:492-537)       */
+int wlk_add_logit_bias(wlk_engine* e, int32_t sid, const int32_t* token_ids, const float* bias, int n);
+/* GreedyDecoder.update (decoding.py:271-287) + _process_cross_attention +
+ * _get_attended_frames (simul_whisper.py:390-437) over the last window_iters decode
+ * calls of the epoch; one device->host copy of 3 scalars per session.                     */
+int wlk_greedy_and_align(wlk_engine* e, const int32_t* sids, int n, int32_t window_iters,
+                         int32_t* token_out, float* logprob_out, int32_t* frame_out);
+
+/* ---- debug taps for parity tests (device -> host fp32) ---------------------------------*/
+int wlk_read_mel(wlk_engine* e, int32_t sid, float* out /* [n_mels,3000] */);
+int wlk_read_encoder(wlk_engine* e, int32_t sid, float* out /* [1500,d] */);
+int wlk_read_logits(wlk_engine* e, int32_t sid, int32_t which /* 0 last, 1 sot row */, float* out /* [V] */);
+int wlk_read_align_attn(wlk_engine* e, int32_t sid, float* out, int64_t capacity, int32_t* rows, int32_t* cols);
+
+/* ---- op-level entry points (kernel tests, roofline benches). Device pointers.
+ *      a_type/w_type/c_type: 0 = fp32, 1 = bf16.  C[M,N] = act(A[M,K] W[N,K]^T + bias)      */
+int wlk_op_gemm(wlk_engine* e, int backend, const void* A, int a_type, int64_t lda,
+                const void* W, int w_type, int64_t ldw, const float* bias,
+                void* C, int c_type, int64_t ldc, int M, int N, int K, int gelu);
+int wlk_op_mel(wlk_engine* e, const float* audio_dev, int64_t n_samples, float* mel_out_dev /* [n_mels,3000] */,
+               int32_t* content_mel_len);
+int wlk_op_encoder_attention(wlk_engine* e, int backend, const void* qkv, int type, int batch, void* out);
+
+/* ---- device timers + per-kernel-class profile (CUDA events on the engine stream) ------- */
+int wlk_timer_record(wlk_engine* e, int slot);                 /* slot in [0,16) */
+int wlk_timer_elapsed_ms(wlk_engine* e, int from_slot, int to_slot, float* ms);
+int wlk_profile_enable(wlk_engine* e, int on);
+int wlk_profile_reset(wlk_engine* e);
+/* class ids: see WLK_KC_*; returns accumulated device ms, launches, algorithmic flops and bytes */
+int wlk_profile_read(wlk_engine* e, int kernel_class, double* ms, int64_t* launches, double* flops, double* bytes);
+int wlk_profile_class_name(int kernel_class, const char** name);
+enum { WLK_KC_MEL = 0, WLK_KC_GEMM_ENC, WLK_KC_ATTN_ENC, WLK_KC_LN, WLK_KC_GEMM_XKV, WLK_KC_GEMM_DEC,
+       WLK_KC_ATTN_DEC_SELF, WLK_KC_ATTN_DEC_CROSS, WLK_KC_LOGITS, WLK_KC_ALIGN, WLK_KC_MISC, WLK_KC_COUNT };
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WLK_B200_H */

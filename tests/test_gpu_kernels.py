@@ -1,0 +1,102 @@
+"""GPU: op-level checks of the hand-written kernels through the C ABI (wlk_op_*),
+against plain torch fp32 references of the same op."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from whisperlivekit_b200.dims import DIMS
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from whisperlivekit_b200.engine import WhisperEngine
+    e = WhisperEngine(DIMS["micro"], None, [(0, 0)], precision="bf16", max_sessions=1, max_batch=1)
+    yield e
+    e.close()
+
+
+def _gemm(eng, backend, A, W, bias, gelu, out_dtype):
+    M, K = A.shape
+    N = W.shape[0]
+    Cm = torch.empty(M, N, device="cuda", dtype=out_dtype)
+    code = {torch.float32: 0, torch.bfloat16: 1}
+    torch.cuda.synchronize()
+    eng.op_gemm(backend, A.data_ptr(), code[A.dtype], A.stride(0), W.data_ptr(), code[W.dtype], W.stride(0),
+                bias.data_ptr() if bias is not None else None, Cm.data_ptr(), code[out_dtype], Cm.stride(0),
+                M, N, K, gelu)
+    eng.sync()
+    return Cm
+
+
+def _ref(A, W, bias, gelu):
+    r = A.float() @ W.float().t()
+    if bias is not None:
+        r = r + bias
+    if gelu:
+        r = torch.nn.functional.gelu(r)
+    return r
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1500, 384, 384), (37, 51, 20), (16, 1280, 1280), (3, 51864, 128)])
+@pytest.mark.parametrize("gelu", [False, True])
+def test_gemm_simt_fp32(eng, M, N, K, gelu):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    out = _gemm(eng, "simt", A, W, b, gelu, torch.float32)
+    ref = _ref(A.double(), W.double(), b.double(), gelu).float() if not gelu else _ref(A, W, b, gelu)
+    assert (out - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
+
+
+SHAPES_TC = [(128, 256, 64), (256, 256, 128), (1500, 1280, 1280), (3000, 384, 240), (1000, 3840, 1280),
+             (129, 264, 72), (64, 128, 5120), (4500, 5120, 1280), (12000, 1280, 5120)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES_TC)
+def test_gemm_tcgen05_bf16(eng, M, N, K):
+    """tcgen05 GEMM vs fp32 reference on the same bf16-rounded operands: only the fp32
+    accumulation order differs, so the bound is tight (1e-3 relative to the output scale)."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    for gelu in (False, True):
+        out = _gemm(eng, "tcgen05", A, W, b, gelu, torch.float32)
+        ref = _ref(A, W, b, gelu)
+        err = (out - ref).abs().max().item()
+        assert err < 1e-3 * max(1.0, ref.abs().max().item()), (M, N, K, gelu, err)
+    out_bf = _gemm(eng, "tcgen05", A, W, b, False, torch.bfloat16)
+    ref = _ref(A, W, b, False)
+    assert (out_bf.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    simt = _gemm(eng, "simt", A, W, b, False, torch.float32)
+    assert (simt - _gemm(eng, "tcgen05", A, W, b, False, torch.float32)).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_tcgen05_strided_overlapping_rows(eng):
+    """The conv stem feeds the GEMM overlapping rows (pitch < row length) through the TMA map."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    base = torch.randn(3002 * 80, device="cuda", generator=g).bfloat16()
+    A = torch.as_strided(base, (3000, 240), (80, 1))
+    W = (torch.randn(384, 240, device="cuda", generator=g) / 15).bfloat16()
+    out = _gemm(eng, "tcgen05", A, W, None, False, torch.float32)
+    ref = A.float() @ W.float().t()
+    assert (out - ref).abs().max().item() < 1e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_encoder_attention_simt(eng, dtype):
+    d, H, B = 128, 2, 2
+    g = torch.Generator(device="cuda").manual_seed(3)
+    qkv = (torch.randn(B * 1500, 3 * d, device="cuda", generator=g) * 0.8).to(dtype)
+    out = torch.empty(B * 1500, d, device="cuda", dtype=dtype)
+    torch.cuda.synchronize()
+    eng.op_encoder_attention("simt", qkv.data_ptr(), 0 if dtype == torch.float32 else 1, B, out.data_ptr())
+    eng.sync()
+    x = qkv.float().view(B, 1500, 3, H, 64)
+    q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
+    ref = (torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v).transpose(1, 2).reshape(B * 1500, d)
+    tol = 2e-5 if dtype == torch.float32 else 1e-2
+    assert (out.float() - ref).abs().max().item() < tol

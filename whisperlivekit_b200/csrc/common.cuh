@@ -1,0 +1,216 @@
+// Shared declarations for the B200 streaming-Whisper engine (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+namespace wlk {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------
+// errors: every C-ABI entry catches and stores a thread-local message
+// ---------------------------------------------------------------------------------
+void set_last_error(const std::string& msg);
+
+struct Error {
+    std::string msg;
+};
+
+#define WLK_CHECK(cond, ...)                                                                   \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            char _b[512];                                                                      \
+            snprintf(_b, sizeof(_b), __VA_ARGS__);                                             \
+            throw ::wlk::Error{std::string(_b) + " [" #cond " @ " __FILE__ ":" +               \
+                               std::to_string(__LINE__) + "]"};                                \
+        }                                                                                      \
+    } while (0)
+
+#define CUDA_CHECK(expr)                                                                       \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            throw ::wlk::Error{std::string("CUDA error: ") + cudaGetErrorString(_e) +          \
+                               " in " #expr " @ " __FILE__ ":" + std::to_string(__LINE__)};    \
+    } while (0)
+
+enum DType { DT_F32 = 0, DT_BF16 = 1 };
+inline size_t dtype_size(int t) { return t == DT_F32 ? 4 : 2; }
+
+// ---------------------------------------------------------------------------------
+// GEMM epilogue description shared by the SIMT and the tcgen05 GEMM kernels.
+//   v = acc + bias[n];  if gelu: v = gelu_erf(v);  if n < scale_cols: v *= col_scale;
+//   if residual: v += residual[m, n];   then stored according to `mode`.
+// ---------------------------------------------------------------------------------
+enum EpiMode {
+    EPI_PLAIN = 0,       // C[m * ldc + n]
+    EPI_XKV = 1,         // cross-K/V head-major scatter: see engine.cu (cross_kv layout)
+    EPI_SELF_QKV = 2,    // decoder self-attn: q -> plain buffer, k/v -> self-KV cache via row map
+    EPI_ROWPTR = 3,      // C row pointers per batch: row m -> batch_ptrs[m / rows_per_batch] + (m % rpb) * ldc
+};
+
+struct Epilogue {
+    const float* bias = nullptr;     // [N] fp32 or null
+    int gelu = 0;
+    float col_scale = 1.f;
+    int scale_cols = 0;              // columns [0, scale_cols) are multiplied by col_scale ...
+    int scale_period = 0;            // ... taken modulo scale_period when it is non-zero
+    const float* residual = nullptr; // fp32 [M, ldr] (may alias C when c_type == fp32)
+    int64_t ldr = 0;
+    void* C = nullptr;
+    int c_type = DT_F32;
+    int64_t ldc = 0;
+    int mode = EPI_PLAIN;
+    // scatter parameters
+    void* const* batch_ptrs = nullptr;   // EPI_XKV / EPI_ROWPTR / EPI_SELF_QKV: per-slot base pointers
+    int rows_per_batch = 1;              // EPI_XKV / EPI_ROWPTR
+    int rows_valid = 1 << 30;            // EPI_ROWPTR: rows with (m % rows_per_batch) >= rows_valid are dropped;
+                                         //             the residual is indexed by the in-batch row
+    int n_head = 0, d_model = 0;         // head-major scatters
+    int kv_len = 0;                      // rows per (layer,kv,head) plane: 1500 (cross) / n_text_ctx (self)
+    int layer = 0;                       // EPI_SELF_QKV
+    const int32_t* row_slot = nullptr;   // EPI_SELF_QKV: row -> index into batch_ptrs
+    const int32_t* row_pos = nullptr;    // EPI_SELF_QKV: row -> position in the self-KV cache
+};
+
+struct GemmArgs {
+    const void* A = nullptr; int a_type = DT_F32; int64_t lda = 0;   // [M, K] row-major (K contiguous)
+    const void* W = nullptr; int w_type = DT_F32; int64_t ldw = 0;   // [N, K] row-major (K contiguous)
+    int M = 0, N = 0, K = 0;
+    Epilogue epi;
+};
+
+void gemm_simt(const GemmArgs& g, cudaStream_t st);
+void gemm_tcgen05(const GemmArgs& g, cudaStream_t st, int num_sms);
+bool gemm_tcgen05_supported(const GemmArgs& g, std::string* why);
+
+// ---------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float gelu_erf(float x) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Apply the arithmetic part of the epilogue to one accumulator element.
+__device__ __forceinline__ float epi_math(const Epilogue& e, float v, int m, int n) {
+    if (e.bias) v += __ldg(e.bias + n);
+    if (e.gelu) v = gelu_erf(v);
+    if ((e.scale_period ? (n % e.scale_period) : n) < e.scale_cols) v *= e.col_scale;
+    if (e.residual) {
+        int rr = (e.mode == EPI_ROWPTR) ? (m % e.rows_per_batch) : m;
+        v += e.residual[(int64_t)rr * e.ldr + n];
+    }
+    return v;
+}
+
+// Destination address (in elements of the output type) for element (m, n); nullptr-safe
+// callers must have checked m < M, n < N.  Returns the base pointer through *base.
+__device__ __forceinline__ int64_t epi_index(const Epilogue& e, int m, int n, void** base) {
+    switch (e.mode) {
+        default:
+        case EPI_PLAIN:
+            *base = e.C;
+            return (int64_t)m * e.ldc + n;
+        case EPI_ROWPTR: {
+            int b = m / e.rows_per_batch, r = m - b * e.rows_per_batch;
+            *base = e.batch_ptrs[b];
+            return (int64_t)r * e.ldc + n;
+        }
+        case EPI_XKV: {
+            // n -> (layer, kv, head, e);  m -> (batch b, frame r)
+            int b = m / e.rows_per_batch, r = m - b * e.rows_per_batch;
+            int two_d = 2 * e.d_model;
+            int l = n / two_d, rem = n - l * two_d;
+            int kv = rem / e.d_model, c = rem - kv * e.d_model;
+            int h = c >> 6, el = c & 63;
+            *base = e.batch_ptrs[b];
+            return ((((int64_t)l * 2 + kv) * e.n_head + h) * e.kv_len + r) * 64 + el;
+        }
+        case EPI_SELF_QKV: {
+            int part = n / e.d_model, c = n - part * e.d_model;
+            if (part == 0) {                       // q: plain [rows, d_model]
+                *base = e.C;
+                return (int64_t)m * e.ldc + c;
+            }
+            int h = c >> 6, el = c & 63;
+            *base = e.batch_ptrs[e.row_slot[m]];
+            return ((((int64_t)e.layer * 2 + (part - 1)) * e.n_head + h) * e.kv_len + e.row_pos[m]) * 64 + el;
+        }
+    }
+}
+
+__device__ __forceinline__ bool epi_row_dropped(const Epilogue& e, int m) {
+    return e.mode == EPI_ROWPTR && (m % e.rows_per_batch) >= e.rows_valid;
+}
+
+__device__ __forceinline__ void epi_store1(const Epilogue& e, int m, int n, float acc) {
+    if (epi_row_dropped(e, m)) return;
+    float v = epi_math(e, acc, m, n);
+    void* base;
+    int64_t idx = epi_index(e, m, n, &base);
+    if (e.c_type == DT_F32) reinterpret_cast<float*>(base)[idx] = v;
+    else reinterpret_cast<bf16*>(base)[idx] = __float2bfloat16_rn(v);
+}
+
+// 8 consecutive columns n0..n0+7 (n0 % 8 == 0, all < N, same head): vector stores.
+__device__ __forceinline__ void epi_store8(const Epilogue& e, int m, int n0, const float* acc) {
+    if (epi_row_dropped(e, m)) return;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = epi_math(e, acc[j], m, n0 + j);
+    void* base;
+    int64_t idx = epi_index(e, m, n0, &base);
+    if (e.c_type == DT_F32) {
+        float* p = reinterpret_cast<float*>(base) + idx;
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+            reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) p[j] = v[j];
+        }
+    } else {
+        bf16* p = reinterpret_cast<bf16*>(base) + idx;
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[2], v[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[6], v[7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0);
+            u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2);
+            u.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(p) = u;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) p[j] = __float2bfloat16_rn(v[j]);
+        }
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace wlk

@@ -1,0 +1,716 @@
+// Non-GEMM kernels of the streaming-Whisper hot path (sm_100a).  Everything here is
+// bandwidth- or latency-bound SIMT code; the tensor-core kernels live in gemm_tc.cu / attn_tc.cu.
+#include "kernels.cuh"
+
+namespace wlk {
+
+// =====================================================================================
+// block reductions
+// =====================================================================================
+template <int NT>
+__device__ __forceinline__ float block_max(float v, float* red) {
+    v = warp_max(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = (threadIdx.x < NT / 32) ? red[threadIdx.x] : -INFINITY;
+    r = warp_max(r);
+    __syncthreads();
+    return r;            // valid in every thread of warp 0 .. broadcast below
+}
+template <int NT>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = (threadIdx.x < NT / 32) ? red[threadIdx.x] : 0.f;
+    r = warp_sum(r);
+    __syncthreads();
+    return r;
+}
+// all-thread broadcast versions
+template <int NT>
+__device__ __forceinline__ float block_max_all(float v, float* red) {
+    float r = block_max<NT>(v, red);
+    if (threadIdx.x == 0) red[0] = r;
+    __syncthreads();
+    r = red[0];
+    __syncthreads();
+    return r;
+}
+template <int NT>
+__device__ __forceinline__ float block_sum_all(float v, float* red) {
+    float r = block_sum<NT>(v, red);
+    if (threadIdx.x == 0) red[0] = r;
+    __syncthreads();
+    r = red[0];
+    __syncthreads();
+    return r;
+}
+
+// =====================================================================================
+// log-mel front end  (reference whisperlivekit/whisper/audio.py:110-157)
+//   pass 1: per 8-frame CTA: reflect-padded framing, Hann window, 400-point real DFT (201 bins),
+//           power, mel projection, log10(clamp 1e-10) -> raw[f][m], per-CTA max
+//   pass 2: global max over the CTA maxima, max(x, gmax-8), (x+4)/4, convert, time-major store
+//           with a zero row either side (the conv stem's padding) and the silence constant for
+//           frames that see only the 30 s of zero padding.
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+mel_power_kernel(const MelJob* __restrict__ jobs, int n_mels, const float* __restrict__ filtT /*[201][n_mels]*/,
+                 const float* __restrict__ window, const float2* __restrict__ twiddle) {
+    constexpr int FR = MEL_FRAMES_PER_CTA;
+    __shared__ float xw[FR][N_FFT];
+    __shared__ float2 tw[N_FFT];
+    __shared__ float pw[FR][N_FREQ + 3];
+    __shared__ float red[8];
+    const MelJob job = jobs[blockIdx.y];
+    const int f0 = blockIdx.x * FR;
+    const int tid = threadIdx.x;
+    const int n_valid = min(job.n_compute, job.n_total);
+    if (f0 >= n_valid) {
+        if (tid == 0) job.blockmax[blockIdx.x] = -10.0f;
+        return;
+    }
+    for (int i = tid; i < N_FFT; i += 256) tw[i] = twiddle[i];
+    for (int i = tid; i < FR * N_FFT; i += 256) {
+        int fr = i / N_FFT, j = i - fr * N_FFT;
+        int s = (f0 + fr) * HOP - N_FFT / 2 + j;       // torch.stft(center=True): reflect pad n_fft/2
+        if (s < 0) s = -s;
+        float x = (s < job.n) ? job.audio[s] : 0.f;     // right of the audio: the appended zeros
+        xw[fr][j] = x * window[j];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < FR * N_FREQ; idx += 256) {
+        int fr = idx / N_FREQ, k = idx - fr * N_FREQ;
+        float re = 0.f, im = 0.f;
+        int t = 0;
+#pragma unroll 4
+        for (int j = 0; j < N_FFT; ++j) {
+            float x = xw[fr][j];
+            float2 c = tw[t];
+            re = fmaf(x, c.x, re);
+            im = fmaf(x, c.y, im);
+            t += k;
+            if (t >= N_FFT) t -= N_FFT;
+        }
+        pw[fr][k] = re * re + im * im;
+    }
+    __syncthreads();
+    float lmax = -INFINITY;
+    for (int idx = tid; idx < FR * n_mels; idx += 256) {
+        int fr = idx / n_mels, m = idx - fr * n_mels;
+        int f = f0 + fr;
+        if (f >= n_valid) continue;
+        float acc = 0.f;
+        for (int k = 0; k < N_FREQ; ++k) acc = fmaf(filtT[k * n_mels + m], pw[fr][k], acc);
+        float v = log10f(fmaxf(acc, 1e-10f));
+        job.raw[(int64_t)f * n_mels + m] = v;
+        lmax = fmaxf(lmax, v);
+    }
+    float bm = block_max<256>(lmax, red);
+    if (tid == 0) job.blockmax[blockIdx.x] = bm;
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(256)
+mel_finalize_kernel(const MelJob* __restrict__ jobs, int n_mels) {
+    __shared__ float red[8];
+    const MelJob job = jobs[blockIdx.y];
+    float m = -10.0f;    // frames inside the zero padding contribute log10(1e-10)
+    for (int i = threadIdx.x; i < MEL_MAX_CTAS; i += 256) m = fmaxf(m, job.blockmax[i]);
+    const float gmax = block_max_all<256>(m, red);
+    const float thr = gmax - 8.0f;
+    const int n_valid = min(job.n_compute, job.n_total);
+    TO* out = reinterpret_cast<TO*>(job.out);
+    const int64_t total = (int64_t)MEL_ROWS * n_mels;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        int r = (int)(i / n_mels);
+        float v = 0.f;
+        if (r >= 1 && r <= N_FRAMES) {
+            int f = r - 1;
+            float raw = (f < n_valid) ? job.raw[(int64_t)f * n_mels + (i - (int64_t)r * n_mels)] : -10.0f;
+            v = (fmaxf(raw, thr) + 4.0f) * 0.25f;
+        }
+        out[i] = from_f32<TO>(v);
+    }
+}
+
+void mel_forward(const MelJob* jobs_dev, int batch, int n_mels, const float* filtT, const float* window,
+                 const float2* twiddle, int out_type, int max_compute_frames, cudaStream_t st) {
+    (void)max_compute_frames;
+    dim3 g1(MEL_MAX_CTAS, batch);
+    mel_power_kernel<<<g1, 256, 0, st>>>(jobs_dev, n_mels, filtT, window, twiddle);
+    CUDA_CHECK(cudaGetLastError());
+    dim3 g2(64, batch);
+    if (out_type == DT_F32) mel_finalize_kernel<float><<<g2, 256, 0, st>>>(jobs_dev, n_mels);
+    else mel_finalize_kernel<bf16><<<g2, 256, 0, st>>>(jobs_dev, n_mels);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// =====================================================================================
+// small utilities
+// =====================================================================================
+template <typename T>
+__global__ void zero_rows_kernel(T* base, int64_t row_elems, const int64_t* rows, int n_rows) {
+    int r = blockIdx.x;
+    if (r >= n_rows) return;
+    T* p = base + rows[r] * row_elems;
+    for (int64_t i = threadIdx.x; i < row_elems; i += blockDim.x) p[i] = from_f32<T>(0.f);
+}
+void zero_rows(void* base, int type, int64_t row_elems, const int64_t* rows, int n_rows, cudaStream_t st) {
+    if (n_rows <= 0) return;
+    if (type == DT_F32) zero_rows_kernel<float><<<n_rows, 256, 0, st>>>((float*)base, row_elems, rows, n_rows);
+    else zero_rows_kernel<bf16><<<n_rows, 256, 0, st>>>((bf16*)base, row_elems, rows, n_rows);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+template <typename T>
+__global__ void cvt_from_f32_kernel(const float* s, T* d, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        d[i] = from_f32<T>(s[i]);
+}
+template <typename T>
+__global__ void cvt_to_f32_kernel(const T* s, float* d, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        d[i] = to_f32(s[i]);
+}
+void convert_f32_to(const float* src, void* dst, int dst_type, int64_t n, cudaStream_t st) {
+    int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+    if (grid < 1) grid = 1;
+    if (dst_type == DT_F32) cvt_from_f32_kernel<float><<<grid, 256, 0, st>>>(src, (float*)dst, n);
+    else cvt_from_f32_kernel<bf16><<<grid, 256, 0, st>>>(src, (bf16*)dst, n);
+    CUDA_CHECK(cudaGetLastError());
+}
+void convert_to_f32(const void* src, int src_type, float* dst, int64_t n, cudaStream_t st) {
+    int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+    if (grid < 1) grid = 1;
+    if (src_type == DT_F32) cvt_to_f32_kernel<float><<<grid, 256, 0, st>>>((const float*)src, dst, n);
+    else cvt_to_f32_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)src, dst, n);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+template <typename T>
+__global__ void pack_conv_kernel(const float* w, T* dst, int c_out, int c_in) {
+    // dst[co][k * c_in + ci] = w[co][ci][k]
+    int64_t n = (int64_t)c_out * c_in * 3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int co = (int)(i / (3 * c_in));
+        int rem = (int)(i - (int64_t)co * 3 * c_in);
+        int k = rem / c_in, ci = rem - k * c_in;
+        dst[i] = from_f32<T>(w[((int64_t)co * c_in + ci) * 3 + k]);
+    }
+}
+void pack_conv_weight(const float* w, void* dst, int dst_type, int c_out, int c_in, cudaStream_t st) {
+    if (dst_type == DT_F32) pack_conv_kernel<float><<<1024, 256, 0, st>>>(w, (float*)dst, c_out, c_in);
+    else pack_conv_kernel<bf16><<<1024, 256, 0, st>>>(w, (bf16*)dst, c_out, c_in);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// =====================================================================================
+// LayerNorm (fp32 statistics, reference whisper/model.py:39-41), one warp per row
+// =====================================================================================
+template <typename TO>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ b,
+                 TO* __restrict__ out, int64_t ldo, int rows, int d, const int32_t* __restrict__ row_index) {
+    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const float* xr = x + (int64_t)(row_index ? row_index[warp] : warp) * ldx;
+    float s = 0.f;
+    for (int i = lane; i < d; i += 32) s += xr[i];
+    const float mean = warp_sum(s) / d;
+    float v = 0.f;
+    for (int i = lane; i < d; i += 32) { float t = xr[i] - mean; v = fmaf(t, t, v); }
+    const float rstd = 1.0f / sqrtf(warp_sum(v) / d + 1e-5f);
+    TO* o = out + (int64_t)warp * ldo;
+    for (int i = lane; i < d; i += 32) o[i] = from_f32<TO>((xr[i] - mean) * rstd * w[i] + b[i]);
+}
+void layernorm(const float* x, int64_t ldx, const float* w, const float* b, void* out, int out_type, int64_t ldo,
+               int rows, int d, const int32_t* row_index, cudaStream_t st) {
+    if (rows <= 0) return;
+    int grid = (rows + 7) / 8;
+    if (out_type == DT_F32) layernorm_kernel<float><<<grid, 256, 0, st>>>(x, ldx, w, b, (float*)out, ldo, rows, d, row_index);
+    else layernorm_kernel<bf16><<<grid, 256, 0, st>>>(x, ldx, w, b, (bf16*)out, ldo, rows, d, row_index);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void embed_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ pos,
+                             const float* __restrict__ emb, const float* __restrict__ pos_emb, float* __restrict__ x,
+                             int rows, int d) {
+    int r = blockIdx.x;
+    if (r >= rows) return;
+    const float* e = emb + (int64_t)tok[r] * d;
+    const float* p = pos_emb + (int64_t)pos[r] * d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) x[(int64_t)r * d + i] = e[i] + p[i];
+}
+void embed_tokens(const int32_t* tokens_dev, const int32_t* pos_dev, const float* emb, const float* pos_emb, float* x,
+                  int rows, int d, cudaStream_t st) {
+    if (rows <= 0) return;
+    embed_kernel<<<rows, 256, 0, st>>>(tokens_dev, pos_dev, emb, pos_emb, x, rows, d);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// =====================================================================================
+// encoder self-attention, SIMT flash-style with fp32 arithmetic
+//   (reference whisper/model.py:148-173: softmax((q s)(k s)^T) v, no mask, all 1500 positions)
+//   grid (ceil(1500/64), H, batch), 256 threads; thread (ty, tx) owns rows ty*4.. x cols tx*4..
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+enc_attn_simt_kernel(const T* __restrict__ qkv, int n_head, int d_model, T* __restrict__ out) {
+    constexpr int BQ = 64, BKV = 64, D = 64, LD = D + 1;
+    extern __shared__ float sm[];
+    float* Qs = sm;                 // [BQ][LD]
+    float* Ks = Qs + BQ * LD;       // [BKV][LD]
+    float* Vs = Ks + BKV * LD;      // [BKV][LD]
+    float* Ps = Vs + BKV * LD;      // [BQ][LD]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+    const int64_t ld = 3 * (int64_t)d_model;
+    const T* base = qkv + (int64_t)b * N_CTX * ld;
+
+    for (int i = tid; i < BQ * D; i += 256) {
+        int r = i >> 6, e = i & 63;
+        int row = q0 + r;
+        Qs[r * LD + e] = (row < N_CTX) ? to_f32(base[(int64_t)row * ld + h * D + e]) : 0.f;
+    }
+    float o[4][4], mrow[4], lrow[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        mrow[i] = -INFINITY; lrow[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+    }
+    for (int k0 = 0; k0 < N_CTX; k0 += BKV) {
+        __syncthreads();
+        for (int i = tid; i < BKV * D; i += 256) {
+            int r = i >> 6, e = i & 63;
+            int row = k0 + r;
+            float kv = 0.f, vv = 0.f;
+            if (row < N_CTX) {
+                kv = to_f32(base[(int64_t)row * ld + d_model + h * D + e]);
+                vv = to_f32(base[(int64_t)row * ld + 2 * d_model + h * D + e]);
+            }
+            Ks[r * LD + e] = kv;
+            Vs[r * LD + e] = vv;
+        }
+        __syncthreads();
+        float s[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 8
+        for (int e = 0; e < D; ++e) {
+            float a[4], c[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = Qs[(ty * 4 + i) * LD + e];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = Ks[(tx * 4 + j) * LD + e];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s[i][j] = fmaf(a[i], c[j], s[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (k0 + tx * 4 + j >= N_CTX) s[i][j] = -INFINITY;
+                mx = fmaxf(mx, s[i][j]);
+            }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            const float mnew = fmaxf(mrow[i], mx);
+            const float corr = expf(mrow[i] - mnew);       // exp(-inf)=0 on the first tile
+            float rs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float p = expf(s[i][j] - mnew);
+                rs += p;
+                Ps[(ty * 4 + i) * LD + tx * 4 + j] = p;
+            }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
+            lrow[i] = lrow[i] * corr + rs;
+            mrow[i] = mnew;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[i][j] *= corr;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int c = 0; c < BKV; ++c) {
+            float p[4], v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) p[i] = Ps[(ty * 4 + i) * LD + c];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = Vs[c * LD + tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[i][j] = fmaf(p[i], v[j], o[i][j]);
+        }
+    }
+    T* ob = out + (int64_t)b * N_CTX * d_model;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int row = q0 + ty * 4 + i;
+        if (row >= N_CTX) continue;
+        float inv = 1.0f / lrow[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ob[(int64_t)row * d_model + h * D + tx * 4 + j] = from_f32<T>(o[i][j] * inv);
+    }
+}
+
+void enc_attention_simt(const void* qkv, int type, int batch, int n_head, int d_model, void* out, cudaStream_t st) {
+    dim3 grid((N_CTX + 63) / 64, n_head, batch);
+    const int smem = 4 * 64 * 65 * 4;
+    static bool set = false;
+    if (!set) {
+        CUDA_CHECK(cudaFuncSetAttribute(enc_attn_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_CHECK(cudaFuncSetAttribute(enc_attn_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        set = true;
+    }
+    if (type == DT_F32) enc_attn_simt_kernel<float><<<grid, 256, smem, st>>>((const float*)qkv, n_head, d_model, (float*)out);
+    else enc_attn_simt_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)qkv, n_head, d_model, (bf16*)out);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// =====================================================================================
+// decoder self-attention over the per-session self-KV cache (causal)
+//   (reference whisper/model.py:109-114,130-146,148-173 with the triu(-inf) mask of :278)
+//   grid (H, jobs), 128 threads; queries processed one after the other
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(128)
+dec_self_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, int layer, int n_head, int d_model,
+                     int n_text_ctx, T* __restrict__ out) {
+    extern __shared__ float sm[];
+    float* sc = sm;                       // [n_text_ctx]
+    float* qs = sc + n_text_ctx;          // [64]
+    float* part = qs + 64;                // [2][64]
+    float* red = part + 128;              // [8]
+    const DecJob job = jobs[blockIdx.y];
+    const int h = blockIdx.x, tid = threadIdx.x;
+    const T* Kc = reinterpret_cast<const T*>(job.self_kv) + (((int64_t)layer * 2 + 0) * n_head + h) * n_text_ctx * 64;
+    const T* Vc = reinterpret_cast<const T*>(job.self_kv) + (((int64_t)layer * 2 + 1) * n_head + h) * n_text_ctx * 64;
+    for (int t = 0; t < job.n_rows; ++t) {
+        const int64_t row = job.row_off + t;
+        const int n_keys = job.offset + t + 1;
+        if (tid < 64) qs[tid] = to_f32(q[row * d_model + h * 64 + tid]);
+        __syncthreads();
+        float lmax = -INFINITY;
+        for (int key = tid; key < n_keys; key += 128) {
+            const T* kr = Kc + (int64_t)key * 64;
+            float s = 0.f;
+#pragma unroll 16
+            for (int e = 0; e < 64; ++e) s = fmaf(qs[e], to_f32(kr[e]), s);
+            sc[key] = s;
+            lmax = fmaxf(lmax, s);
+        }
+        const float m = block_max_all<128>(lmax, red);
+        float lsum = 0.f;
+        for (int key = tid; key < n_keys; key += 128) {
+            float p = expf(sc[key] - m);
+            sc[key] = p;
+            lsum += p;
+        }
+        const float l = block_sum_all<128>(lsum, red);
+        const int g = tid >> 6, e = tid & 63;
+        float acc = 0.f;
+        for (int key = g; key < n_keys; key += 2) acc = fmaf(sc[key], to_f32(Vc[(int64_t)key * 64 + e]), acc);
+        part[g * 64 + e] = acc;
+        __syncthreads();
+        if (tid < 64) out[row * d_model + h * 64 + tid] = from_f32<T>((part[tid] + part[64 + tid]) / l);
+        __syncthreads();
+    }
+}
+void dec_self_attention(const void* q, int type, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model,
+                        int n_text_ctx, void* out, cudaStream_t st) {
+    dim3 grid(n_head, n_jobs);
+    int smem = (n_text_ctx + 64 + 128 + 8) * 4;
+    if (type == DT_F32) dec_self_attn_kernel<float><<<grid, 128, smem, st>>>((const float*)q, jobs, layer, n_head, d_model, n_text_ctx, (float*)out);
+    else dec_self_attn_kernel<bf16><<<grid, 128, smem, st>>>((const bf16*)q, jobs, layer, n_head, d_model, n_text_ctx, (bf16*)out);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// =====================================================================================
+// decoder cross-attention over the persistent cross-K/V (1500 frames), with the alignment
+// export: for alignment heads the softmaxed rows go to the session's alignment ring
+//   (reference whisper/model.py:116-128,148-173; AlignAtt reads softmax(qk) of those heads,
+//    simul_whisper.py:401-416)
+//   grid (H, jobs), 256 threads, 8 queries per pass
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+dec_cross_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, int layer, int n_head, int d_model,
+                      int n_text_ctx, const int32_t* __restrict__ align_rank, T* __restrict__ out) {
+    constexpr int QB = 8;
+    extern __shared__ float sm[];
+    float* sc = sm;                          // [QB][1500]
+    float* qs = sc + QB * N_CTX;             // [QB][64]
+    float* part = qs + QB * 64;              // [4][QB][64]
+    const DecJob job = jobs[blockIdx.y];
+    const int h = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const T* Kc = reinterpret_cast<const T*>(job.cross_kv) + (((int64_t)layer * 2 + 0) * n_head + h) * N_CTX * 64;
+    const T* Vc = reinterpret_cast<const T*>(job.cross_kv) + (((int64_t)layer * 2 + 1) * n_head + h) * N_CTX * 64;
+    const int rank = align_rank[layer * n_head + h];
+    for (int t0 = 0; t0 < job.n_rows; t0 += QB) {
+        const int nq = min(QB, job.n_rows - t0);
+        for (int i = tid; i < QB * 64; i += 256) {
+            int qi = i >> 6, e = i & 63;
+            qs[i] = (qi < nq) ? to_f32(q[(int64_t)(job.row_off + t0 + qi) * d_model + h * 64 + e]) : 0.f;
+        }
+        __syncthreads();
+        for (int key = tid; key < N_CTX; key += 256) {
+            const T* kr = Kc + (int64_t)key * 64;
+            float s[QB];
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) s[qi] = 0.f;
+#pragma unroll 8
+            for (int e = 0; e < 64; ++e) {
+                float kv = to_f32(kr[e]);
+#pragma unroll
+                for (int qi = 0; qi < QB; ++qi) s[qi] = fmaf(qs[qi * 64 + e], kv, s[qi]);
+            }
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) sc[qi * N_CTX + key] = s[qi];
+        }
+        __syncthreads();
+        // softmax: warp w normalises query row w (QB == number of warps)
+        if (warp < nq) {
+            float* r = sc + warp * N_CTX;
+            float mx = -INFINITY;
+            for (int k = lane; k < N_CTX; k += 32) mx = fmaxf(mx, r[k]);
+            mx = warp_max(mx);
+            float sum = 0.f;
+            for (int k = lane; k < N_CTX; k += 32) { float p = expf(r[k] - mx); r[k] = p; sum += p; }
+            sum = warp_sum(sum);
+            const float inv = 1.0f / sum;
+            float* arow = (rank >= 0)
+                ? job.align + ((int64_t)rank * n_text_ctx + job.align_row0 + t0 + warp) * N_CTX : nullptr;
+            for (int k = lane; k < N_CTX; k += 32) {
+                float p = r[k] * inv;
+                r[k] = p;
+                if (arow) arow[k] = p;
+            }
+        }
+        __syncthreads();
+        {
+            const int g = tid >> 6, e = tid & 63;
+            float acc[QB];
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) acc[qi] = 0.f;
+            for (int key = g; key < N_CTX; key += 4) {
+                float v = to_f32(Vc[(int64_t)key * 64 + e]);
+#pragma unroll
+                for (int qi = 0; qi < QB; ++qi) acc[qi] = fmaf(sc[qi * N_CTX + key], v, acc[qi]);
+            }
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) part[(g * QB + qi) * 64 + e] = acc[qi];
+        }
+        __syncthreads();
+        for (int i = tid; i < nq * 64; i += 256) {
+            int qi = i >> 6, e = i & 63;
+            float v = part[(0 * QB + qi) * 64 + e] + part[(1 * QB + qi) * 64 + e] + part[(2 * QB + qi) * 64 + e] +
+                      part[(3 * QB + qi) * 64 + e];
+            out[(int64_t)(job.row_off + t0 + qi) * d_model + h * 64 + e] = from_f32<T>(v);
+        }
+        __syncthreads();
+    }
+}
+void dec_cross_attention(const void* q, int type, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model,
+                         int n_text_ctx, const int32_t* align_rank, void* out, cudaStream_t st) {
+    dim3 grid(n_head, n_jobs);
+    const int smem = (8 * N_CTX + 8 * 64 + 4 * 8 * 64) * 4;
+    static bool set = false;
+    if (!set) {
+        CUDA_CHECK(cudaFuncSetAttribute(dec_cross_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_CHECK(cudaFuncSetAttribute(dec_cross_attn_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        set = true;
+    }
+    if (type == DT_F32) dec_cross_attn_kernel<float><<<grid, 256, smem, st>>>((const float*)q, jobs, layer, n_head, d_model, n_text_ctx, align_rank, (float*)out);
+    else dec_cross_attn_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)q, jobs, layer, n_head, d_model, n_text_ctx, align_rank, (bf16*)out);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// =====================================================================================
+// logits post-processing (reference simul_whisper.py:370-385, whisper/decoding.py:271-287)
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+no_speech_kernel(const LogitJob* __restrict__ jobs, int n_vocab, int no_speech_token, StepResult* __restrict__ res) {
+    __shared__ float red[8];
+    const float* lg = jobs[blockIdx.x].logits_sot;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < n_vocab; i += 256) mx = fmaxf(mx, lg[i]);
+    mx = block_max_all<256>(mx, red);
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n_vocab; i += 256) s += expf(lg[i] - mx);
+    s = block_sum_all<256>(s, red);
+    if (threadIdx.x == 0) res[blockIdx.x].no_speech = expf(lg[no_speech_token] - mx) / s;
+}
+void no_speech_prob(const LogitJob* jobs, int n, int n_vocab, int no_speech_token, StepResult* res, cudaStream_t st) {
+    no_speech_kernel<<<n, 256, 0, st>>>(jobs, n_vocab, no_speech_token, res);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void suppress_kernel(const LogitJob* __restrict__ jobs, const int32_t* __restrict__ toks, int n_tokens) {
+    float* lg = jobs[blockIdx.x].logits_last;
+    for (int i = threadIdx.x; i < n_tokens; i += blockDim.x) lg[toks[i]] = -INFINITY;
+}
+void suppress_tokens(const LogitJob* jobs, int n, const int32_t* tokens_dev, int n_tokens, cudaStream_t st) {
+    if (n_tokens <= 0) return;
+    suppress_kernel<<<n, 128, 0, st>>>(jobs, tokens_dev, n_tokens);
+    CUDA_CHECK(cudaGetLastError());
+}
+__global__ void bias_kernel(float* lg, const int32_t* toks, const float* bias, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lg[toks[i]] += bias[i];
+}
+void add_logit_bias(float* logits, const int32_t* tokens_dev, const float* bias_dev, int n, cudaStream_t st) {
+    if (n <= 0) return;
+    bias_kernel<<<(n + 127) / 128, 128, 0, st>>>(logits, tokens_dev, bias_dev, n);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256)
+greedy_kernel(const LogitJob* __restrict__ jobs, int n_vocab, StepResult* __restrict__ res) {
+    __shared__ float red[8];
+    __shared__ int redi[8];
+    const float* lg = jobs[blockIdx.x].logits_last;
+    float mx = -INFINITY;
+    int arg = 0x7fffffff;
+    for (int i = threadIdx.x; i < n_vocab; i += 256) {
+        float v = lg[i];
+        if (v > mx) { mx = v; arg = i; }          // strictly greater: keeps the first index per thread
+    }
+    // argmax with lowest-index tie break (torch.argmax returns the first maximal element)
+    for (int off = 16; off > 0; off >>= 1) {
+        float om = __shfl_xor_sync(0xffffffffu, mx, off);
+        int oa = __shfl_xor_sync(0xffffffffu, arg, off);
+        if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+    }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = mx; redi[threadIdx.x >> 5] = arg; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (red[w] > mx || (red[w] == mx && redi[w] < arg)) { mx = red[w]; arg = redi[w]; }
+        red[0] = mx; redi[0] = arg;
+    }
+    __syncthreads();
+    mx = red[0]; arg = redi[0];
+    __syncthreads();
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n_vocab; i += 256) s += expf(lg[i] - mx);
+    s = block_sum_all<256>(s, red);
+    if (threadIdx.x == 0) {
+        res[blockIdx.x].token = arg;
+        res[blockIdx.x].logprob = -logf(s);       // log_softmax at the argmax = mx - (mx + log s)
+    }
+}
+void greedy_pick(const LogitJob* jobs, int n, int n_vocab, StepResult* res, cudaStream_t st) {
+    greedy_kernel<<<n, 256, 0, st>>>(jobs, n_vocab, res);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// =====================================================================================
+// AlignAtt reduction (reference simul_whisper.py:418-437 + whisper/timing.py:19-54)
+//   stats : per (head, frame) mean and 1/(std+1e-8) over the retained token rows (unbiased=False)
+//   rows  : normalise, reflect-padded median-7 over frames, mean over heads, keep [:content_len]
+//   argmax: most attended frame of the last row
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+align_stats_kernel(const LogitJob* __restrict__ jobs, int n_text_ctx) {
+    const LogitJob job = jobs[blockIdx.z];
+    const int a = blockIdx.y, f = blockIdx.x * 256 + threadIdx.x;
+    if (f >= N_CTX) return;
+    const float* p = job.align + (int64_t)a * n_text_ctx * N_CTX + f;
+    const int T = job.row_end - job.row_begin;
+    float s = 0.f;
+    for (int r = job.row_begin; r < job.row_end; ++r) s += p[(int64_t)r * N_CTX];
+    const float mean = s / T;
+    float v = 0.f;
+    for (int r = job.row_begin; r < job.row_end; ++r) { float d = p[(int64_t)r * N_CTX] - mean; v = fmaf(d, d, v); }
+    const float sd = sqrtf(v / T);
+    job.stats[((int64_t)a * N_CTX + f) * 2 + 0] = mean;
+    job.stats[((int64_t)a * N_CTX + f) * 2 + 1] = 1.0f / (sd + 1e-8f);
+}
+
+__device__ __forceinline__ void cswap(float& a, float& b) { float lo = fminf(a, b), hi = fmaxf(a, b); a = lo; b = hi; }
+__device__ __forceinline__ float median7(float* v) {
+    // 7-input sorting network (16 compare-exchanges); v[3] is the median afterwards
+    cswap(v[0], v[6]); cswap(v[2], v[3]); cswap(v[4], v[5]);
+    cswap(v[0], v[2]); cswap(v[1], v[4]); cswap(v[3], v[6]);
+    cswap(v[0], v[1]); cswap(v[2], v[5]); cswap(v[3], v[4]);
+    cswap(v[1], v[2]); cswap(v[4], v[6]);
+    cswap(v[2], v[3]); cswap(v[4], v[5]);
+    cswap(v[1], v[2]); cswap(v[3], v[4]); cswap(v[5], v[6]);
+    return v[3];
+}
+
+__global__ void __launch_bounds__(256)
+align_rows_kernel(const LogitJob* __restrict__ jobs, int n_align, int n_text_ctx) {
+    const LogitJob job = jobs[blockIdx.z];
+    const int T = job.row_end - job.row_begin;
+    const int n_out = job.full ? T : 1;
+    if ((int)blockIdx.y >= n_out) return;
+    const int r = job.full ? (job.row_begin + blockIdx.y) : (job.row_end - 1);
+    const int f = blockIdx.x * 256 + threadIdx.x;
+    if (f >= job.content_len) return;
+    float acc = 0.f;
+    for (int a = 0; a < n_align; ++a) {
+        const float* p = job.align + ((int64_t)a * n_text_ctx + r) * N_CTX;
+        const float* st = job.stats + (int64_t)a * N_CTX * 2;
+        float v[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            int g = f + j - 3;
+            if (g < 0) g = -g;                           // reflect (no edge repeat), F.pad(mode="reflect")
+            if (g >= N_CTX) g = 2 * (N_CTX - 1) - g;
+            v[j] = (p[g] - st[g * 2]) * st[g * 2 + 1];
+        }
+        acc += median7(v);
+    }
+    job.attn_out[(int64_t)(r - job.row_begin) * N_CTX + f] = acc / n_align;
+}
+
+__global__ void __launch_bounds__(256)
+align_argmax_kernel(const LogitJob* __restrict__ jobs, StepResult* __restrict__ res) {
+    __shared__ float red[8];
+    __shared__ int redi[8];
+    const LogitJob job = jobs[blockIdx.x];
+    const int T = job.row_end - job.row_begin;
+    const float* row = job.attn_out + (int64_t)(T - 1) * N_CTX;
+    float mx = -INFINITY;
+    int arg = 0x7fffffff;
+    for (int i = threadIdx.x; i < job.content_len; i += 256) {
+        float v = row[i];
+        if (v > mx) { mx = v; arg = i; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        float om = __shfl_xor_sync(0xffffffffu, mx, off);
+        int oa = __shfl_xor_sync(0xffffffffu, arg, off);
+        if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+    }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = mx; redi[threadIdx.x >> 5] = arg; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (red[w] > mx || (red[w] == mx && redi[w] < arg)) { mx = red[w]; arg = redi[w]; }
+        res[blockIdx.x].frame = (arg == 0x7fffffff) ? 0 : arg;
+    }
+}
+
+void align_reduce(const LogitJob* jobs, int n, int n_align, int n_text_ctx, StepResult* res, cudaStream_t st) {
+    dim3 g1((N_CTX + 255) / 256, n_align, n);
+    align_stats_kernel<<<g1, 256, 0, st>>>(jobs, n_text_ctx);
+    CUDA_CHECK(cudaGetLastError());
+    dim3 g2((N_CTX + 255) / 256, n_text_ctx, n);      // rows beyond the retained window exit immediately
+    align_rows_kernel<<<g2, 256, 0, st>>>(jobs, n_align, n_text_ctx);
+    CUDA_CHECK(cudaGetLastError());
+    align_argmax_kernel<<<n, 256, 0, st>>>(jobs, res);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace wlk

@@ -1,0 +1,85 @@
+// Host-callable launchers of the non-GEMM kernels (mel front end, LayerNorm, encoder / decoder
+// attention, logits post-processing, AlignAtt reduction).  `type` is a wlk::DType: the activation
+// type of the engine's precision mode.
+#pragma once
+#include "common.cuh"
+
+namespace wlk {
+
+constexpr int MEL_ROWS = 3002;      // 3000 frames + one zero row either side (conv padding)
+constexpr int N_FRAMES = 3000;
+constexpr int N_CTX = 1500;
+constexpr int N_FREQ = 201;
+constexpr int N_FFT = 400;
+constexpr int HOP = 160;
+constexpr int MEL_FRAMES_PER_CTA = 8;
+constexpr int MEL_MAX_CTAS = (N_FRAMES + 2 + MEL_FRAMES_PER_CTA - 1) / MEL_FRAMES_PER_CTA;   // 376
+
+struct MelJob {                 // one per session in the batch (device array)
+    const float* audio;         // device, n samples
+    float* raw;                 // [MEL_ROWS-2 + 2][n_mels] fp32 log10(max(mel,1e-10)) for frames < n_compute
+    float* blockmax;            // [MEL_MAX_CTAS]
+    void* out;                  // [MEL_ROWS][n_mels] activation type, time-major, zero pad rows
+    int32_t n;                  // samples
+    int32_t n_compute;          // frames whose window touches audio (others are the silence constant)
+    int32_t n_total;            // floor((n + 480000) / 160): frames the reference's STFT keeps
+    int32_t pad;
+};
+
+void mel_forward(const MelJob* jobs_dev, int batch, int n_mels, const float* filters, const float* window,
+                 const float2* twiddle, int out_type, int max_compute_frames, cudaStream_t st);
+
+void zero_rows(void* base, int type, int64_t row_elems, const int64_t* row_index_dev, int n_rows, cudaStream_t st);
+
+void layernorm(const float* x, int64_t ldx, const float* w, const float* b, void* out, int out_type, int64_t ldo,
+               int rows, int d, const int32_t* row_index_dev, cudaStream_t st);
+
+void embed_tokens(const int32_t* tokens_dev, const int32_t* pos_dev, const float* emb, const float* pos_emb, float* x,
+                  int rows, int d, cudaStream_t st);
+
+// encoder self-attention over the fused qkv buffer [batch*1500, 3d] (q,k pre-scaled by d_head^-0.25)
+void enc_attention_simt(const void* qkv, int type, int batch, int n_head, int d_model, void* out, cudaStream_t st);
+void enc_attention_tcgen05(const void* qkv, int batch, int n_head, int d_model, void* out, cudaStream_t st, int num_sms);
+
+struct DecJob {                 // one per session in a decode batch (device array)
+    void* self_kv;              // [L][2][H][n_text_ctx][64]
+    const void* cross_kv;       // [L][2][H][1500][64]
+    float* align;               // [n_align][n_text_ctx][1500] softmaxed cross-attention rows
+    float* logits_last;         // [V]
+    float* logits_sot;          // [V]
+    int32_t row_off;            // first row of this session in the packed row buffers
+    int32_t n_rows;             // Tq
+    int32_t offset;             // self-KV length before this call (position of row 0)
+    int32_t align_row0;         // first alignment row this call writes (rows accumulated in the epoch)
+};
+
+void dec_self_attention(const void* q, int type, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model,
+                        int n_text_ctx, void* out, cudaStream_t st);
+// align_rank[layer * n_head + head] = rank of the alignment head or -1
+void dec_cross_attention(const void* q, int type, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model,
+                         int n_text_ctx, const int32_t* align_rank, void* out, cudaStream_t st);
+
+struct LogitJob {               // one per session (device array)
+    float* logits_last;
+    float* logits_sot;
+    const float* align;         // [n_align][n_text_ctx][1500]
+    float* attn_out;            // [n_text_ctx][1500] scratch/tap: processed attention rows
+    float* stats;               // [n_align][1500][2] scratch: mean, 1/(std+1e-8)
+    int32_t row_begin, row_end; // retained alignment rows [begin, end)
+    int32_t content_len;
+    int32_t full;               // 1: produce every retained row (debug tap); 0: last row only
+};
+struct StepResult { int32_t token; float logprob; int32_t frame; float no_speech; };
+
+void no_speech_prob(const LogitJob* jobs, int n, int n_vocab, int no_speech_token, StepResult* res, cudaStream_t st);
+void suppress_tokens(const LogitJob* jobs, int n, const int32_t* tokens_dev, int n_tokens, cudaStream_t st);
+void add_logit_bias(float* logits, const int32_t* tokens_dev, const float* bias_dev, int n, cudaStream_t st);
+void greedy_pick(const LogitJob* jobs, int n, int n_vocab, StepResult* res, cudaStream_t st);
+void align_reduce(const LogitJob* jobs, int n, int n_align, int n_text_ctx, StepResult* res, cudaStream_t st);
+
+void convert_f32_to(const float* src, void* dst, int dst_type, int64_t n, cudaStream_t st);
+void convert_to_f32(const void* src, int src_type, float* dst, int64_t n, cudaStream_t st);
+// conv weight [c_out, c_in, 3] -> [c_out, 3 * c_in] (tap-major) in the destination type
+void pack_conv_weight(const float* w, void* dst, int dst_type, int c_out, int c_in, cudaStream_t st);
+
+}  // namespace wlk

@@ -1,0 +1,230 @@
+"""Python host wrapper over the C-ABI engine (include/wlk_b200.h).
+
+``WhisperEngine`` exposes the session API the AlignAtt host code drives
+(``alignatt.StreamingAlignAtt`` / ``AlignAttHooks``); every method is one C call
+into hand-written sm_100a CUDA.  Inputs are host numpy arrays (the reference's
+callers hand CPU float32 PCM); device memory is owned by the
+engine.  There is no fallback path: construction raises without the library or
+without a B200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+from .dims import ModelDimensions, SpecialTokens, default_alignment_heads
+from .weights import hann_window, mel_filterbank
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class WhisperEngine:
+    backend = "b200-cuda"
+
+    def __init__(self, dims: ModelDimensions, state_dict: Optional[Dict[str, np.ndarray]] = None,
+                 align_heads: Optional[Sequence[Tuple[int, int]]] = None, *, precision: str = "bf16",
+                 device: int = 0, max_sessions: int = 8, max_batch: int = 8,
+                 gemm_backend: str = "auto", attn_backend: str = "auto"):
+        self.lib = L.load()
+        self.dims = dims
+        self.specials = SpecialTokens.for_dims(dims)
+        self.precision = precision
+        heads = list(align_heads) if align_heads is not None else default_alignment_heads(dims)
+        self.align_heads = [tuple(int(v) for v in h) for h in heads]
+        be = {"auto": L.BACKEND_AUTO, "simt": L.BACKEND_SIMT, "tcgen05": L.BACKEND_TCGEN05}
+        cdims = L.wlk_dims(*dims.as_tuple())
+        cfg = L.wlk_config(device=device, precision={"fp32": L.PREC_FP32, "bf16": L.PREC_BF16}[precision],
+                           max_sessions=max_sessions, max_batch=max_batch,
+                           gemm_backend=be[gemm_backend], attn_backend=be[attn_backend],
+                           max_align_heads=max(len(self.align_heads), 1), reserved=0)
+        self.max_batch = max_batch
+        h = C.c_void_p()
+        L.check(self.lib.wlk_engine_create(C.byref(cdims), C.byref(cfg), C.byref(h)))
+        self.h = h
+        self._closed = False
+        self.load_tensor("mel_filters", mel_filterbank(dims.n_mels))
+        self.load_tensor("hann_window", hann_window())
+        pairs = _i32(self.align_heads).reshape(-1)
+        L.check(self.lib.wlk_engine_set_alignment_heads(self.h, pairs.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                        len(self.align_heads)))
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    # -- weights -----------------------------------------------------------------
+    def load_tensor(self, name: str, arr) -> None:
+        a = np.ascontiguousarray(np.asarray(arr, dtype=np.float32))
+        shape = (C.c_int64 * a.ndim)(*a.shape)
+        L.check(self.lib.wlk_engine_load_tensor(self.h, name.encode(), _ptr(a), shape, a.ndim))
+
+    def load_state_dict(self, sd: Dict[str, np.ndarray]) -> None:
+        for k, v in sd.items():
+            if k.endswith("alignment_heads") or k.endswith(".mask"):
+                continue
+            self.load_tensor(k, v)
+        L.check(self.lib.wlk_engine_finalize_weights(self.h))
+
+    def weight_blob(self) -> Tuple[int, int]:
+        """(device pointer, nbytes) of the packed weights -- broadcast target for NCCL at init."""
+        p, n = C.c_void_p(), C.c_size_t()
+        L.check(self.lib.wlk_engine_weight_blob(self.h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def adopt_weights(self) -> None:
+        L.check(self.lib.wlk_engine_adopt_weights(self.h))
+
+    def memory(self) -> Dict[str, int]:
+        w, s, k = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        L.check(self.lib.wlk_engine_memory(self.h, C.byref(w), C.byref(s), C.byref(k)))
+        return dict(weights=w.value, sessions=s.value, workspace=k.value)
+
+    def stream(self) -> int:
+        p = C.c_void_p()
+        L.check(self.lib.wlk_engine_stream(self.h, C.byref(p)))
+        return int(p.value or 0)
+
+    def sync(self) -> None:
+        L.check(self.lib.wlk_engine_sync(self.h))
+
+    # -- sessions ------------------------------------------------------------------
+    def open_session(self) -> int:
+        sid = C.c_int32()
+        L.check(self.lib.wlk_session_open(self.h, C.byref(sid)))
+        return int(sid.value)
+
+    def close_session(self, sid: int) -> None:
+        L.check(self.lib.wlk_session_close(self.h, sid))
+
+    def append_audio(self, sid: int, pcm) -> None:
+        a = np.ascontiguousarray(np.asarray(pcm, dtype=np.float32).reshape(-1))
+        L.check(self.lib.wlk_session_append_audio(self.h, sid, _ptr(a), a.shape[0]))
+
+    def drop_audio(self, sid: int, n: int) -> None:
+        L.check(self.lib.wlk_session_drop_audio(self.h, sid, int(n)))
+
+    def clear_audio(self, sid: int) -> None:
+        L.check(self.lib.wlk_session_clear_audio(self.h, sid))
+
+    def audio_len(self, sid: int) -> int:
+        n = C.c_int64()
+        L.check(self.lib.wlk_session_audio_len(self.h, sid, C.byref(n)))
+        return int(n.value)
+
+    # -- hot path --------------------------------------------------------------------
+    def encode(self, sids: Sequence[int]) -> List[int]:
+        s = _i32(sids)
+        out = np.zeros(len(s), np.int32)
+        L.check(self.lib.wlk_encode(self.h, _ptr(s), len(s), _ptr(out)))
+        return [int(v) for v in out]
+
+    def decode(self, sids: Sequence[int], tokens: Sequence[Sequence[int]], sot_index: int = 0) -> None:
+        s = _i32(sids)
+        offs = np.zeros(len(s) + 1, np.int32)
+        offs[1:] = np.cumsum([len(t) for t in tokens])
+        flat = _i32([t for ts in tokens for t in ts])
+        L.check(self.lib.wlk_decode(self.h, _ptr(s), len(s), _ptr(flat), _ptr(offs), int(sot_index)))
+
+    def no_speech_prob(self, sids: Sequence[int]) -> List[float]:
+        s = _i32(sids)
+        out = np.zeros(len(s), np.float32)
+        L.check(self.lib.wlk_no_speech_prob(self.h, _ptr(s), len(s), _ptr(out)))
+        return [float(v) for v in out]
+
+    def suppress(self, sids: Sequence[int], token_ids: Sequence[int]) -> None:
+        s, t = _i32(sids), _i32(token_ids)
+        L.check(self.lib.wlk_suppress(self.h, _ptr(s), len(s), _ptr(t), len(t)))
+
+    def add_logit_bias(self, sid: int, token_ids: Sequence[int], biases: Sequence[float]) -> None:
+        t = _i32(token_ids)
+        b = np.ascontiguousarray(np.asarray(biases, np.float32))
+        L.check(self.lib.wlk_add_logit_bias(self.h, int(sid), _ptr(t), _ptr(b), len(t)))
+
+    def greedy_and_align(self, sids: Sequence[int], window_iters: int = 16):
+        s = _i32(sids)
+        tok = np.zeros(len(s), np.int32)
+        lp = np.zeros(len(s), np.float32)
+        fr = np.zeros(len(s), np.int32)
+        L.check(self.lib.wlk_greedy_and_align(self.h, _ptr(s), len(s), int(window_iters), _ptr(tok), _ptr(lp), _ptr(fr)))
+        return [(int(tok[i]), float(lp[i]), int(fr[i])) for i in range(len(s))]
+
+    # -- debug taps -------------------------------------------------------------------
+    def read_mel(self, sid: int) -> np.ndarray:
+        out = np.zeros((self.dims.n_mels, 3000), np.float32)
+        L.check(self.lib.wlk_read_mel(self.h, sid, _ptr(out)))
+        return out
+
+    def read_encoder(self, sid: int) -> np.ndarray:
+        out = np.zeros((1500, self.dims.n_audio_state), np.float32)
+        L.check(self.lib.wlk_read_encoder(self.h, sid, _ptr(out)))
+        return out
+
+    def read_logits(self, sid: int) -> np.ndarray:
+        out = np.zeros(self.dims.n_vocab, np.float32)
+        L.check(self.lib.wlk_read_logits(self.h, sid, 0, _ptr(out)))
+        return out
+
+    def read_sot_logits(self, sid: int) -> np.ndarray:
+        out = np.zeros(self.dims.n_vocab, np.float32)
+        L.check(self.lib.wlk_read_logits(self.h, sid, 1, _ptr(out)))
+        return out
+
+    def read_align_attn(self, sid: int) -> np.ndarray:
+        cap = self.dims.n_text_ctx * 1500
+        out = np.zeros(cap, np.float32)
+        r, c = C.c_int32(), C.c_int32()
+        L.check(self.lib.wlk_read_align_attn(self.h, sid, _ptr(out), cap, C.byref(r), C.byref(c)))
+        return out[: r.value * c.value].reshape(r.value, c.value).copy()
+
+    # -- timers / profile ---------------------------------------------------------------
+    def timer_record(self, slot: int) -> None:
+        L.check(self.lib.wlk_timer_record(self.h, slot))
+
+    def timer_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        L.check(self.lib.wlk_timer_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return float(ms.value)
+
+    def profile_enable(self, on: bool) -> None:
+        L.check(self.lib.wlk_profile_enable(self.h, int(on)))
+
+    def profile_reset(self) -> None:
+        L.check(self.lib.wlk_profile_reset(self.h))
+
+    def profile_read(self) -> Dict[str, dict]:
+        out = {}
+        for i, name in enumerate(L.KERNEL_CLASSES):
+            ms, n, fl, by = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
+            L.check(self.lib.wlk_profile_read(self.h, i, C.byref(ms), C.byref(n), C.byref(fl), C.byref(by)))
+            out[name] = dict(ms=ms.value, launches=n.value, flops=fl.value, bytes=by.value)
+        return out
+
+    # -- op-level (device pointers, e.g. torch tensors' data_ptr()) ----------------------
+    def op_gemm(self, backend: str, A_ptr, a_type, lda, W_ptr, w_type, ldw, bias_ptr, C_ptr, c_type, ldc,
+                M, N, K, gelu=False):
+        be = {"simt": L.BACKEND_SIMT, "tcgen05": L.BACKEND_TCGEN05}[backend]
+        L.check(self.lib.wlk_op_gemm(self.h, be, A_ptr, a_type, lda, W_ptr, w_type, ldw, bias_ptr, C_ptr, c_type,
+                                     ldc, M, N, K, int(gelu)))
+
+    def op_encoder_attention(self, backend: str, qkv_ptr, dtype_code, batch, out_ptr):
+        be = {"simt": L.BACKEND_SIMT, "tcgen05": L.BACKEND_TCGEN05}[backend]
+        L.check(self.lib.wlk_op_encoder_attention(self.h, be, qkv_ptr, dtype_code, batch, out_ptr))
+
+    # -- lifetime ------------------------------------------------------------------------
+    def close(self) -> None:
+        if not self._closed:
+            self._closed = True
+            L.check(self.lib.wlk_engine_destroy(self.h))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
