@@ -76,6 +76,9 @@ int wlk_session_append_audio(wlk_engine* e, int32_t sid, const float* pcm_host, 
 int wlk_session_drop_audio(wlk_engine* e, int32_t sid, int64_t n_front_samples);
 int wlk_session_clear_audio(wlk_engine* e, int32_t sid);
 int wlk_session_audio_len(wlk_engine* e, int32_t sid, int64_t* n);
+/* DecoderState.clean_cache (reference decoder_state.py:51-59): forget the self-KV and the
+ * alignment rows of the current epoch but keep the encoder output / cross-K/V.           */
+int wlk_session_reset_decoder(wlk_engine* e, int32_t sid);
 
 /* ---- hot path, batched over sessions -------------------------------------------------
  * wlk_encode: AlignAtt._encode (simul_whisper.py:299-352) = log_mel_spectrogram

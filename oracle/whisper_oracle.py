@@ -301,6 +301,11 @@ class OracleEngine:
     def audio_len(self, sid: int) -> int:
         return int(self._s[sid]["audio"].shape[0])
 
+    def reset_decoder(self, sid: int) -> None:
+        s = self._s[sid]
+        s["kv"], s["iters"], s["logits"], s["sot_row"] = {}, [], None, None
+        # the reference's clean_cache drops the cross K/V too; they are recomputed from the same xa
+
     # -- hot path ---------------------------------------------------------
     @torch.no_grad()
     def encode(self, sids: Sequence[int]) -> List[int]:

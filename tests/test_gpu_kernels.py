@@ -100,3 +100,25 @@ def test_encoder_attention_simt(eng, dtype):
     ref = (torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v).transpose(1, 2).reshape(B * 1500, d)
     tol = 2e-5 if dtype == torch.float32 else 1e-2
     assert (out.float() - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("d,H,B", [(128, 2, 1), (384, 6, 2), (1280, 20, 1)])
+def test_encoder_attention_tcgen05(eng, d, H, B):
+    """Fused tcgen05 attention vs fp32 softmax(QK^T)V on the same bf16 inputs.  P is rounded to
+    bf16 before the PV product (8 mantissa bits): tolerance 2e-2 on outputs of O(1)."""
+    from whisperlivekit_b200.dims import ModelDimensions
+    from whisperlivekit_b200.engine import WhisperEngine
+    e2 = WhisperEngine(ModelDimensions(80, 1500, d, H, 1, 51864, 448, 64, 1, 1), None, [(0, 0)], precision="bf16",
+                       max_sessions=1, max_batch=1)
+    g = torch.Generator(device="cuda").manual_seed(d)
+    qkv = (torch.randn(B * 1500, 3 * d, device="cuda", generator=g) * 0.8).bfloat16()
+    out = torch.full((B * 1500, d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    e2.op_encoder_attention("tcgen05", qkv.data_ptr(), 1, B, out.data_ptr())
+    e2.sync()
+    x = qkv.float().view(B, 1500, 3, H, 64)
+    q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
+    ref = (torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v).transpose(1, 2).reshape(B * 1500, d)
+    assert not torch.isnan(out.float()).any()
+    assert (out.float() - ref).abs().max().item() < 2e-2
+    e2.close()

@@ -190,9 +190,49 @@ def check_large_timing():
     eng.close()
 
 
+def check_attn_tc():
+    import torch
+    from whisperlivekit_b200.dims import ModelDimensions
+    from whisperlivekit_b200.engine import WhisperEngine
+    for (d, H, B) in [(64, 1, 1), (128, 2, 1), (1280, 20, 2)]:
+        eng = WhisperEngine(ModelDimensions(80, 1500, d, H, 1, 51864, 448, 64, 1, 1), None, [(0, 0)], precision="bf16",
+                            max_sessions=1, max_batch=1)
+        g = torch.Generator(device="cuda").manual_seed(d)
+        qkv = (torch.randn(B * 1500, 3 * d, device="cuda", generator=g) * 0.8).bfloat16()
+        out = torch.full((B * 1500, d), float("nan"), device="cuda", dtype=torch.bfloat16)
+        out_s = torch.empty_like(out)
+        torch.cuda.synchronize()
+        eng.op_encoder_attention("tcgen05", qkv.data_ptr(), 1, B, out.data_ptr())
+        eng.op_encoder_attention("simt", qkv.data_ptr(), 1, B, out_s.data_ptr())
+        eng.sync()
+        x = qkv.float().view(B, 1500, 3, H, 64)
+        q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
+        ref = (torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v).transpose(1, 2).reshape(B * 1500, d)
+        err = torch.nan_to_num((out.float() - ref).abs(), nan=1e9)
+        rows = [err[i:i + 128].max().item() for i in range(0, 1500, 128)]
+        cols = [err[:, j:j + 16].max().item() for j in range(0, 64, 16)]
+        emit(check="attn_tc", shape=[d, H, B], max_err=err.max().item(), nan=int(torch.isnan(out.float()).sum().item()),
+             simt_err=(out_s.float() - ref).abs().max().item(), err_by_qtile=rows, err_by_dh16=cols,
+             sample_out=out[0, :4].float().tolist(), sample_ref=ref[0, :4].tolist(),
+             sample_out_r200=out[200, :4].float().tolist(), sample_ref_r200=ref[200, :4].tolist())
+        if d == 1280:
+            for name in ("tcgen05", "simt"):
+                for _ in range(2):
+                    eng.op_encoder_attention(name, qkv.data_ptr(), 1, B, out.data_ptr())
+                eng.timer_record(0)
+                for _ in range(5):
+                    eng.op_encoder_attention(name, qkv.data_ptr(), 1, B, out.data_ptr())
+                eng.timer_record(1)
+                ms = eng.timer_elapsed_ms(0, 1) / 5
+                emit(check="attn_time", backend=name, shape=[d, H, B], ms=ms,
+                     tflops=4.0 * B * H * 1500 * 1500 * 64 / ms / 1e9)
+        eng.close()
+
+
 CHECKS = {
     "gemm_simt": check_gemm_simt,
     "gemm_tc": check_gemm_tc,
+    "attn_tc": check_attn_tc,
     "engine_fp32": lambda: check_engine("fp32"),
     "policy_fp32": check_policy_fp32,
     "engine_bf16_simt": lambda: check_engine("bf16", "simt"),

@@ -54,6 +54,7 @@ SIGNATURES = {
     "wlk_session_drop_audio": (C.c_int, [_vp, C.c_int32, C.c_int64]),
     "wlk_session_clear_audio": (C.c_int, [_vp, C.c_int32]),
     "wlk_session_audio_len": (C.c_int, [_vp, C.c_int32, _i64p]),
+    "wlk_session_reset_decoder": (C.c_int, [_vp, C.c_int32]),
     "wlk_encode": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "wlk_decode": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int32]),
     "wlk_no_speech_prob": (C.c_int, [_vp, _vp, C.c_int, _vp]),

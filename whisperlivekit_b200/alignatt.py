@@ -270,3 +270,235 @@ class StreamingAlignAtt:
         if not self.closed:
             self.engine.close_session(self.sid)
             self.closed = True
+
+
+# =============================================================================================
+# Drop-in hooks for the reference's own AlignAttBase.infer()
+# =============================================================================================
+class _EncoderFeature:
+    """What AlignAttBase.infer treats opaquely: `encoder_feature[:, :content_mel_len, :]`
+    (align_att_base.py:193) and pass-through to the hooks.  The tensor stays on the device."""
+
+    def __init__(self, engine, sid, content_len=None):
+        self.engine, self.sid, self.content_len = engine, sid, content_len
+        self.shape = (1, 1500, engine.dims.n_audio_state)
+        self.ndim = 3
+
+    def __getitem__(self, key):
+        c = self.content_len
+        if isinstance(key, tuple) and len(key) >= 2 and isinstance(key[1], slice) and key[1].stop is not None:
+            c = key[1].stop
+        return _EncoderFeature(self.engine, self.sid, c)
+
+    def numpy(self):
+        a = self.engine.read_encoder(self.sid)[None]
+        return a if self.content_len is None else a[:, : self.content_len]
+
+
+class _Logits:
+    """Return value of _get_logits_and_cross_attn: the base class only does `logits[:, -1, :]`."""
+
+    def __init__(self, engine, sid):
+        self.engine, self.sid = engine, sid
+
+    def __getitem__(self, key):
+        return self
+
+    def numpy(self):
+        return self.engine.read_logits(self.sid)[None]
+
+
+class AlignAttHooks:
+    """Engine-backed implementation of every abstract hook of the reference's AlignAttBase
+    (align_att_base.py:541-649).  Mixed in front of AlignAttBase by plugin.make_b200_alignatt_class();
+    token tensors stay CPU torch.LongTensors (the base class slices them and calls .tolist()),
+    everything heavy stays on the device behind one C call per hook."""
+
+    def __init__(self, cfg, loaded_model=None, mlx_encoder=None, fw_encoder=None):
+        from whisperlivekit.simul_whisper.decoder_state import DecoderState
+        self.engine = loaded_model.engine
+        self.device = "cpu"
+        self.mlx_encoder, self.fw_encoder = None, None
+        self._base_init(cfg, loaded_model)
+        self.state = DecoderState()
+        self.sid = self.engine.open_session()
+        self._frame = 0
+        self._n_audio = 0
+        self._init_state(cfg)
+
+    def __del__(self):
+        try:
+            self.engine.close_session(self.sid)
+        except Exception:
+            pass
+
+    # ---- state -----------------------------------------------------------------
+    def _init_state(self, cfg):
+        from whisperlivekit.simul_whisper.eow_detection import load_cif
+        self._init_state_common(cfg)
+        self.state.CIFLinear, self.state.always_fire, self.state.never_fire = load_cif(
+            cfg, n_audio_state=self.model.dims.n_audio_state, device="cpu")
+        self.state.num_align_heads = len(self.engine.align_heads)
+        t = self.tokenizer
+        sup = [t.transcribe, t.translate, t.sot, t.sot_prev, t.sot_lm, t.no_timestamps] + list(t.all_language_tokens)
+        if t.no_speech is not None:
+            sup.append(t.no_speech)
+        self._suppress = sorted(set(sup))                         # simul_whisper.py:161-172
+        self._blank = list(t.encode(" ")) + [t.eot]
+        self.init_tokens()
+        self.init_context()
+        self.state.decoder_type = cfg.decoder_type
+        if cfg.decoder_type != "greedy":
+            raise NotImplementedError("the B200 AlignAtt backend implements greedy decoding (beams=1)")
+
+    def init_tokens(self):
+        import torch
+        self.state.initial_tokens = torch.tensor(self.tokenizer.sot_sequence_including_notimestamps,
+                                                 dtype=torch.long).unsqueeze(0)
+        self.state.initial_token_length = self.state.initial_tokens.shape[1]
+        self.state.sot_index = self.tokenizer.sot_sequence.index(self.tokenizer.sot)
+        self.state.tokens = [self.state.initial_tokens]
+
+    def init_context(self):
+        from whisperlivekit.simul_whisper.token_buffer import TokenBuffer
+        kw = dict(tokenizer=self.tokenizer, device="cpu", prefix_token_ids=[self.tokenizer.sot_prev])
+        self.state.context = TokenBuffer.empty(**kw)
+        if self.cfg.static_init_prompt is not None:
+            self.state.context = TokenBuffer.from_text(self.cfg.static_init_prompt, **kw)
+        if self.cfg.init_prompt is not None:
+            self.state.context.text += self.cfg.init_prompt
+
+    # ---- audio window (simul_whisper.py:219-237), mirrored into the device ring -------------
+    def insert_audio(self, segment=None):
+        if segment is not None:
+            self.state.segments.append(segment)
+            self.engine.append_audio(self.sid, np.asarray(segment, dtype=np.float32))
+        removed_len = 0
+        segments_len = self.segments_len()
+        while len(self.state.segments) > 1 and segments_len > self.cfg.audio_max_len:
+            removed_len = self.state.segments[0].shape[0] / 16000
+            segments_len -= removed_len
+            self.state.last_attend_frame -= int(TOKENS_PER_SECOND * removed_len)
+            self.state.cumulative_time_offset += removed_len
+            self.engine.drop_audio(self.sid, int(self.state.segments[0].shape[0]))
+            self.state.segments = self.state.segments[1:]
+            if len(self.state.tokens) > 1:
+                self.state.context.append_token_ids(self.state.tokens[1][0, :].tolist())
+                self.state.tokens = [self.state.initial_tokens] + self.state.tokens[2:]
+        return removed_len
+
+    def refresh_segment(self, complete=False):
+        n_before = sum(int(s.shape[0]) for s in self.state.segments)
+        super().refresh_segment(complete=complete)
+        n_after = sum(int(s.shape[0]) for s in self.state.segments)
+        if n_after == 0:
+            self.engine.clear_audio(self.sid)
+        elif n_after < n_before:
+            self.engine.drop_audio(self.sid, n_before - n_after)
+
+    def _concat_segments(self):
+        return sum(int(s.shape[0]) for s in self.state.segments)      # the audio itself is already on the device
+
+    def _current_tokens(self):
+        import torch
+        toks = self.state.tokens
+        if not self.state.context.is_empty():
+            toks = [self.state.context.as_tensor_beam(1, device="cpu")] + toks
+        return torch.cat(toks, dim=1) if len(toks) > 1 else toks[0]
+
+    def fire_at_boundary(self, feature):
+        if self.state.always_fire:
+            return True
+        if self.state.never_fire:
+            return False
+        if self.state.CIFLinear is None:
+            return False
+        import torch
+        from whisperlivekit.simul_whisper.eow_detection import fire_at_boundary
+        return fire_at_boundary(torch.from_numpy(feature.numpy()), self.state.CIFLinear)
+
+    # ---- hot-path hooks -----------------------------------------------------------
+    def _encode(self, input_segments):
+        n = self.engine.audio_len(self.sid)
+        if n != input_segments:
+            raise RuntimeError(f"device audio ring ({n}) out of sync with state.segments ({input_segments})")
+        content = self.engine.encode([self.sid])[0]
+        self._iters = 0
+        return _EncoderFeature(self.engine, self.sid), content
+
+    def lang_id(self, encoder_features):
+        self.engine.reset_decoder(self.sid)
+        self.engine.decode([self.sid], [[self.tokenizer.sot]], sot_index=0)
+        lg = self.engine.read_logits(self.sid).astype(np.float64)
+        toks = list(self.tokenizer.all_language_tokens)
+        sel = lg[toks]
+        p = np.exp(sel - sel.max())
+        p /= p.sum()
+        probs = {c: float(p[j]) for j, c in enumerate(self.tokenizer.all_language_codes)}
+        self._clean_cache()
+        return [toks[int(np.argmax(sel))]], [probs]
+
+    def _clean_cache(self):
+        self.engine.reset_decoder(self.sid)
+
+    def _init_sum_logprobs(self):
+        return [0.0]
+
+    def _get_logits_and_cross_attn(self, tokens, encoder_feature):
+        self.engine.decode([self.sid], [tokens[0].tolist()], sot_index=self.state.sot_index)
+        self._iters += 1
+        return _Logits(self.engine, self.sid), self._iters
+
+    def _check_no_speech(self, logits):
+        if self.tokenizer.no_speech is not None:
+            return self.engine.no_speech_prob([self.sid])[0] > self.cfg.nonspeech_prob
+        return False
+
+    def _suppress_blank_tokens(self, logits):
+        self.engine.suppress([self.sid], self._blank)
+        return logits
+
+    def _apply_token_suppression(self, logits):
+        self.engine.suppress([self.sid], self._suppress)
+        return logits
+
+    def _apply_dry_penalty(self, logits, current_tokens):
+        pen = dry_penalties(current_tokens[0].tolist(), self.tokenizer.eot)
+        if pen:
+            self.engine.add_logit_bias(self.sid, [t for t, _ in pen], [-a for _, a in pen])
+        return logits
+
+    def _update_tokens(self, current_tokens, logits, sum_logprobs):
+        import torch
+        tok, lp, frame = self.engine.greedy_and_align([self.sid], window_iters=16)[0]
+        eot = self.tokenizer.eot
+        if int(current_tokens[0, -1]) == eot:                       # decoding.py:280-282
+            tok = eot
+        else:
+            sum_logprobs[0] += lp
+        self._frame = frame
+        tokens = torch.cat([current_tokens, torch.tensor([[tok]], dtype=torch.long)], dim=-1)
+        return tokens, tok == eot
+
+    def _process_cross_attention(self, accumulated_cross_attns, content_mel_len):
+        return self._frame                                          # computed with the token, one D2H for both
+
+    def _get_attended_frames(self, attn):
+        return [int(attn)], int(attn)
+
+    def _is_special_token(self, current_tokens):
+        return int(current_tokens[0, -2]) >= DEC_PAD
+
+    def _rewind_tokens(self):
+        import torch
+        return torch.cat(self.state.tokens, dim=1) if len(self.state.tokens) > 0 else self.state.tokens[0]
+
+    def _tokens_to_list(self, current_tokens, start_col):
+        return current_tokens[0, start_col:].flatten().tolist()
+
+    def _make_new_tokens_tensor(self, hypothesis):
+        import torch
+        return torch.tensor([hypothesis], dtype=torch.long)
+
+    def _evaluate(self, tensor):
+        pass

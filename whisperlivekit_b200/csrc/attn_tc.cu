@@ -1,10 +1,248 @@
-// tcgen05 encoder self-attention (placeholder until the fused kernel lands; fails loudly).
+// Fused encoder self-attention on the 5th-gen tensor cores (sm_100a).
+//   O = softmax(Q K^T) V over all 1500 positions, no mask (reference whisper/model.py:148-173);
+//   q and k arrive pre-scaled by d_head^-0.25 from the QKV GEMM epilogue.
+//
+// One CTA per (128-query tile, head, stream); two CTAs are co-resident per SM (80 KB smem, 256 TMEM
+// columns each) so one CTA's exponentials overlap the other's MMAs.
+//   warp 0     TMA producer : Q tile once, then 128-key K and V tiles (128B-swizzled) through a
+//                             2-stage mbarrier ring, straight out of the fused [rows, 3d] qkv buffer
+//   warp 1     MMA issuer   : S = Q K^T   (tcgen05.mma SS, M128 N128 K16 x4)      -> TMEM cols [0,128)
+//                             O_j = P V   (tcgen05.mma TS: P from TMEM, V MN-major smem, N64, K16 x8)
+//                                                                                  -> TMEM cols [128,192)
+//   warps 2-5  softmax      : thread = query row. tcgen05.ld S in 32-column chunks (two passes: row max,
+//                             then exp2 / row sum), P packed to bf16 and written back to TMEM
+//                             (cols [192,256)) with tcgen05.st, running O kept in registers and rescaled
+//                             online; final O / l stored as bf16.
+#include <cudaTypedefs.h>
+
 #include "kernels.cuh"
+#include "ptx.cuh"
 
 namespace wlk {
 
-void enc_attention_tcgen05(const void*, int, int, int, void*, cudaStream_t, int) {
-    WLK_CHECK(false, "enc_attention_tcgen05 is not built in this revision; use WLK_BACKEND_SIMT for attention");
+bool make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                       uint32_t box_rows, uint32_t box_cols, std::string* err);
+
+namespace {
+
+constexpr int BQ = 128, BKV = 128, DH = 64;
+constexpr int ATT_THREADS = 192;
+constexpr uint32_t TILE_BYTES = BQ * DH * 2;          // 16 KB: Q, K and V tiles all are 128 x 64 bf16
+constexpr uint32_t SM_Q = 0, SM_K = TILE_BYTES, SM_V = 3 * TILE_BYTES, SM_BAR = 5 * TILE_BYTES;
+constexpr uint32_t ATT_SMEM = SM_BAR + 128 + 1024;
+constexpr uint32_t TM_S = 0, TM_O = 128, TM_P = 192, TM_COLS = 256;
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+        "%15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, int n_head, int d_model, bf16* __restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - ptx::smem_u32(smem_raw));
+    const uint32_t bar_q = sbase + SM_BAR;
+    const uint32_t bar_kv_full = bar_q + 8;       // [2]
+    const uint32_t bar_kv_empty = bar_q + 24;     // [2]
+    const uint32_t bar_s_full = bar_q + 40;
+    const uint32_t bar_s_free = bar_q + 48;
+    const uint32_t bar_p_full = bar_q + 56;
+    const uint32_t bar_o_full = bar_q + 64;
+    const uint32_t tmem_slot = bar_q + 72;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sgen + SM_BAR + 72);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+    const int row0 = b * N_CTX;                          // first row of this stream in the qkv buffer
+    constexpr int NT = (N_CTX + BKV - 1) / BKV;          // 12 key tiles
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tm);
+        ptx::mbar_init(bar_q, 1);
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_kv_full + 8 * i, 1); ptx::mbar_init(bar_kv_empty + 8 * i, 1); }
+        ptx::mbar_init(bar_s_full, 1);
+        ptx::mbar_init(bar_s_free, 128);
+        ptx::mbar_init(bar_p_full, 128);
+        ptx::mbar_init(bar_o_full, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, TM_COLS); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot_gen;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            ptx::mbar_arrive_expect_tx(bar_q, TILE_BYTES);
+            ptx::tma_load_2d(sbase + SM_Q, &tm, bar_q, h * DH, row0 + q0);
+            for (int j = 0; j < NT; ++j) {
+                const uint32_t s = j & 1, ph = (j >> 1) & 1;
+                ptx::mbar_wait(bar_kv_empty + 8 * s, ph ^ 1);
+                ptx::mbar_arrive_expect_tx(bar_kv_full + 8 * s, 2 * TILE_BYTES);
+                ptx::tma_load_2d(sbase + SM_K + s * TILE_BYTES, &tm, bar_kv_full + 8 * s, d_model + h * DH, row0 + j * BKV);
+                ptx::tma_load_2d(sbase + SM_V + s * TILE_BYTES, &tm, bar_kv_full + 8 * s, 2 * d_model + h * DH, row0 + j * BKV);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(BQ, BKV, 0, 0);   // A=Q K-major, B=K K-major
+        constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(BQ, DH, 0, 1);    // A=P (TMEM), B=V MN-major
+        ptx::mbar_wait(bar_q, 0);
+        for (int j = 0; j < NT; ++j) {
+            const uint32_t s = j & 1, ph = (j >> 1) & 1;
+            ptx::mbar_wait(bar_kv_full + 8 * s, ph);
+            ptx::mbar_wait(bar_s_free, (j & 1) ^ 1);          // softmax threads have read S of tile j-1
+            ptx::tc_fence_after();
+            if (lane == 0) {
+                const uint64_t dq = ptx::umma_desc_kmajor_sw128(sbase + SM_Q);
+                const uint64_t dk = ptx::umma_desc_kmajor_sw128(sbase + SM_K + s * TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < DH / 16; ++k)
+                    ptx::umma_bf16_ss(tmem + TM_S, dq + 2 * k, dk + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                ptx::umma_commit(bar_s_full);
+            }
+            __syncwarp();
+            ptx::mbar_wait(bar_p_full, j & 1);                // P of tile j is in TMEM, O_{j-1} was consumed
+            ptx::tc_fence_after();
+            if (lane == 0) {
+                const uint64_t dv = ptx::umma_desc_mnmajor_sw128(sbase + SM_V + s * TILE_BYTES, BKV * 128);
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k)             // 16 keys = 16 V rows of 128 B = 2048 B = +128 encoded
+                    umma_bf16_ts(tmem + TM_O, tmem + TM_P + 8 * k, dv + 128 * k, idesc_o, k > 0 ? 1u : 0u);
+                ptx::umma_commit(bar_o_full);
+                ptx::umma_commit(bar_kv_empty + 8 * s);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int qd = warp & 3;
+        const int r = qd * 32 + lane;                         // query row within the tile == TMEM lane
+        const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+        float acc[DH];
+#pragma unroll
+        for (int e = 0; e < DH; ++e) acc[e] = 0.f;
+        float m = -INFINITY, l = 0.f;                         // running max (log2 domain) and sum
+        for (int j = 0; j < NT; ++j) {
+            const int n_valid = min(BKV, N_CTX - j * BKV);
+            ptx::mbar_wait(bar_s_full, j & 1);
+            ptx::tc_fence_after();
+            // pass 1: row max
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < BKV / 32; ++c) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(tmem + lane_addr + TM_S + c * 32, v);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c * 32 + i < n_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+            }
+            const float m_new = fmaxf(m, mx * LOG2E);
+            const float alpha = exp2f(m - m_new);
+            // O_{j-1} (computed against the previous max) joins the accumulator before rescaling
+            if (j > 0) {
+                ptx::mbar_wait(bar_o_full, (j - 1) & 1);
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < DH / 32; ++c) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(tmem + lane_addr + TM_O + c * 32, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[c * 32 + i] += __uint_as_float(v[i]);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < DH; ++e) acc[e] *= alpha;
+            // pass 2: probabilities, row sum, pack to bf16 into the P region
+            float rs = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < BKV / 32; ++c) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(tmem + lane_addr + TM_S + c * 32, v);
+                ptx::tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float p0 = (c * 32 + 2 * i < n_valid) ? exp2f(fmaf(__uint_as_float(v[2 * i]), LOG2E, -m_new)) : 0.f;
+                    float p1 = (c * 32 + 2 * i + 1 < n_valid) ? exp2f(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, -m_new)) : 0.f;
+                    __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+                    // the row sum uses the rounded values the tensor core will multiply
+                    rs += __low2float(hb) + __high2float(hb);
+                    pk[i] = *reinterpret_cast<uint32_t*>(&hb);
+                }
+                tmem_st_32x16(tmem + lane_addr + TM_P + c * 16, pk);
+            }
+            ptx::tmem_st_wait();
+            l = l * alpha + rs;
+            m = m_new;
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(bar_s_free);     // S fully consumed: next Q K^T may overwrite it
+            ptx::mbar_arrive(bar_p_full);     // P written, O_{j-1} read: P V may run
+        }
+        ptx::mbar_wait(bar_o_full, (NT - 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < DH / 32; ++c) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(tmem + lane_addr + TM_O + c * 32, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[c * 32 + i] += __uint_as_float(v[i]);
+        }
+        if (q0 + r < N_CTX) {
+            const float inv = 1.0f / l;
+            bf16* o = out + (int64_t)(row0 + q0 + r) * d_model + h * DH;
+#pragma unroll
+            for (int e8 = 0; e8 < DH / 8; ++e8) {
+                uint4 u;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[e8 * 8 + 0] * inv, acc[e8 * 8 + 1] * inv);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(acc[e8 * 8 + 2] * inv, acc[e8 * 8 + 3] * inv);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[e8 * 8 + 4] * inv, acc[e8 * 8 + 5] * inv);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(acc[e8 * 8 + 6] * inv, acc[e8 * 8 + 7] * inv);
+                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+                reinterpret_cast<uint4*>(o)[e8] = u;
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem, TM_COLS);
+}
+
+}  // namespace
+
+void enc_attention_tcgen05(const void* qkv, int batch, int n_head, int d_model, void* out, cudaStream_t st, int num_sms) {
+    (void)num_sms;
+    CUtensorMap tm;
+    std::string err;
+    WLK_CHECK(make_tmap_bf16_2d(&tm, qkv, (uint64_t)batch * N_CTX, (uint64_t)3 * d_model, (uint64_t)3 * d_model, BQ, DH, &err),
+              "qkv tensor map: %s", err.c_str());
+    static bool set = false;
+    if (!set) {
+        CUDA_CHECK(cudaFuncSetAttribute(enc_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+        set = true;
+    }
+    dim3 grid((N_CTX + BQ - 1) / BQ, n_head, batch);
+    enc_attn_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm, n_head, d_model, reinterpret_cast<bf16*>(out));
+    CUDA_CHECK(cudaGetLastError());
 }
 
 }  // namespace wlk

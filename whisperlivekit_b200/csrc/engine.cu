@@ -95,6 +95,7 @@ struct wlk_engine {
     int64_t* pad_rows_dev = nullptr;          // rows of h1 to re-zero after the conv1 GEMM
     void** xptrs_dev = nullptr;               // x + b*1500*d
     float* audio_scratch = nullptr;
+    float* mel_scratch = nullptr;             // fp32 [MEL_ROWS][n_mels] for the read_mel tap
     // decoder workspace
     int dec_rows_max = 0;
     float* dx = nullptr; void *dxn = nullptr, *dq = nullptr, *datt = nullptr, *dhid = nullptr, *dsel = nullptr;
@@ -356,7 +357,7 @@ void run_gemm(wlk_engine* e, GemmArgs& g, int cls) {
     ProfScope ps(e, cls, 2.0 * g.M * (double)g.N * g.K,
                  (double)g.M * g.K * dtype_size(g.a_type) + (double)g.N * g.K * dtype_size(g.w_type) +
                      (double)g.M * g.N * dtype_size(g.epi.c_type));
-    bool tc = e->gemm_backend == WLK_BACKEND_TCGEN05 && g.M >= 64 && gemm_tcgen05_supported(g, nullptr);
+    bool tc = e->gemm_backend == WLK_BACKEND_TCGEN05 && gemm_tcgen05_supported(g, nullptr);
     if (tc) gemm_tcgen05(g, e->st, e->num_sms);
     else gemm_simt(g, e->st);
 }
@@ -710,6 +711,7 @@ void create_engine(const wlk_dims* dims, const wlk_config* cfg, wlk_engine** out
     e->att = dmalloc_bytes((size_t)B * N_CTX * d * es, acct);
     e->hid = dmalloc_bytes((size_t)B * N_CTX * 4 * d * es, acct);
     e->audio_scratch = dmalloc<float>(e, AUDIO_CAP, acct);
+    e->mel_scratch = dmalloc<float>(e, (size_t)MEL_ROWS * D.n_mels, acct);
     {
         std::vector<int64_t> rows(2 * B);
         std::vector<void*> xp(B);
@@ -746,7 +748,7 @@ void create_engine(const wlk_dims* dims, const wlk_config* cfg, wlk_engine** out
 void destroy_engine(wlk_engine* e) {
     cudaStreamSynchronize(e->st);
     for (auto& s : e->sess) if (s.open) free_session(e, s);
-    void* ptrs[] = {e->arena.base, e->stage_f32, e->mel_t, e->h1, e->x, e->xn, e->qkv, e->att, e->hid, e->audio_scratch,
+    void* ptrs[] = {e->arena.base, e->stage_f32, e->mel_t, e->h1, e->x, e->xn, e->qkv, e->att, e->hid, e->audio_scratch, e->mel_scratch,
                     e->pad_rows_dev, e->xptrs_dev, e->dx, e->dxn, e->dq, e->datt, e->dhid, e->dsel, e->stg_dev,
                     e->res_dev, e->align_rank_dev};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -938,6 +940,14 @@ int wlk_session_audio_len(wlk_engine* e, int32_t sid, int64_t* n) {
     WLK_API_END
 }
 
+int wlk_session_reset_decoder(wlk_engine* e, int32_t sid) {
+    WLK_API_BEGIN
+    LOCK(e);
+    Session& s = get_session(e, sid);
+    s.self_len = 0; s.align_rows = 0; s.iter_row_start.clear();
+    WLK_API_END
+}
+
 int wlk_encode(wlk_engine* e, const int32_t* sids, int n, int32_t* content_out) {
     WLK_API_BEGIN
     LOCK(e);
@@ -1045,7 +1055,7 @@ int wlk_read_mel(wlk_engine* e, int32_t sid, float* out) {
     const int64_t N = s.audio_len;
     int64_t n_compute = (N + 199) / HOP + 1;
     if (n_compute > N_FRAMES + 2) n_compute = N_FRAMES + 2;
-    float* scratch = e->x;             // fp32, >= 3002*128 floats
+    float* scratch = e->mel_scratch;
     mj[0].audio = s.audio; mj[0].raw = s.mel_raw; mj[0].blockmax = s.mel_blockmax; mj[0].out = scratch;
     mj[0].n = (int32_t)N; mj[0].n_compute = (int32_t)n_compute; mj[0].n_total = (int32_t)((N + 480000) / HOP); mj[0].pad = 0;
     sg.upload();

@@ -57,7 +57,9 @@ template <int BN, int STAGES>
 struct SmemLayout {
     static constexpr uint32_t A_BYTES = BM * BK * 2;
     static constexpr uint32_t B_BYTES = BN * BK * 2;
-    static constexpr uint32_t BAR_OFF = STAGES * (A_BYTES + B_BYTES);
+    static constexpr uint32_t STG_OFF = STAGES * (A_BYTES + B_BYTES);     // epilogue transpose staging
+    static constexpr uint32_t STG_BYTES = 4 * 32 * 33 * 4;                // 4 warps x [32][33] fp32
+    static constexpr uint32_t BAR_OFF = STG_OFF + STG_BYTES;
     static constexpr uint32_t TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
     static constexpr uint32_t DYN = TOTAL + 1024;   // slack for manual 1024-byte alignment
 };
@@ -152,37 +154,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
+        // tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns at a time).  Storing
+        // that directly makes every warp store touch 32 different rows; instead each warp transposes its
+        // 32x32 block through a private padded smem tile so that lanes walk consecutive COLUMNS of one row:
+        // 64-128 B contiguous per warp instruction for every epilogue mode (plain, residual, KV scatter).
         const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-        const bool vec_ok = (N % 8) == 0;
+        float* stg = reinterpret_cast<float*>(smem_gen + L::STG_OFF) + q * (32 * 33);
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m_blk = tile % num_m, n_blk = tile / num_m;
             const uint32_t as = it & 1, ap = (it >> 1) & 1;
             ptx::mbar_wait(bar_tfull + 8 * as, ap);
             ptx::tc_fence_after();
-            const int row = m_blk * BM + q * 32 + lane;
+            const int row_base = m_blk * BM + q * 32;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, r);
                 ptx::tmem_ld_wait();
-                if (row < M) {
-                    const int nb = n_blk * BN + c * 32;
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        const int n0 = nb + j8 * 8;
-                        float v[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j8 * 8 + j]);
-                        if (vec_ok && n0 + 8 <= N) {
-                            epi_store8(epi, row, n0, v);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                if (n0 + j < N) epi_store1(epi, row, n0 + j, v[j]);
-                        }
-                    }
+                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+                __syncwarp();
+                const int n = n_blk * BN + c * 32 + lane;
+                if (n < N) {
+                    const int rows = min(32, M - row_base);
+#pragma unroll 4
+                    for (int i = 0; i < rows; ++i) epi_store1(epi, row_base + i, n, stg[i * 33 + lane]);
                 }
+                __syncwarp();
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_tempty + 8 * as);

@@ -118,6 +118,9 @@ class WhisperEngine:
         L.check(self.lib.wlk_session_audio_len(self.h, sid, C.byref(n)))
         return int(n.value)
 
+    def reset_decoder(self, sid: int) -> None:
+        L.check(self.lib.wlk_session_reset_decoder(self.h, sid))
+
     # -- hot path --------------------------------------------------------------------
     def encode(self, sids: Sequence[int]) -> List[int]:
         s = _i32(sids)

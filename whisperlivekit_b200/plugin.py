@@ -1,0 +1,79 @@
+"""Registration of the B200 engine behind WhisperLiveKit's SimulStreaming/AlignAtt seam.
+
+Needs WhisperLiveKit importable (it is not a dependency of the engine itself).  Nothing in
+WhisperLiveKit is modified on disk: ``install()`` swaps the ``AlignAtt`` symbol that
+``SimulStreamingOnlineProcessor._create_alignatt`` instantiates
+(reference simul_whisper/backend.py:61-71) and wraps ``SimulStreamingASR.load_model``
+(backend.py:530-553) so the weights it loads are packed into a ``WhisperEngine``.
+``core.py``, the AlignAtt policy (``AlignAttBase.infer``), ``SimulStreamingOnlineProcessor`` and
+``tokens_alignment.py`` run unchanged.  See INTEGRATION.md.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+from .dims import ModelDimensions
+from .weights import state_dict_from_torch
+
+
+class B200WhisperModel:
+    """What AlignAttBase / SimulStreamingASR read from ``shared_model``:
+    ``dims``, ``len(decoder.blocks)``, ``num_languages``, ``is_multilingual``, ``device``."""
+
+    class _Decoder:
+        def __init__(self, n):
+            self.blocks = [None] * n
+
+    def __init__(self, engine):
+        self.engine = engine
+        self.dims = engine.dims
+        self.decoder = self._Decoder(engine.dims.n_text_layer)
+        self.device = "cpu"                      # host-side token tensors live on the CPU
+
+    @property
+    def is_multilingual(self):
+        return self.dims.is_multilingual
+
+    @property
+    def num_languages(self):
+        return self.dims.num_languages
+
+
+def engine_from_torch_whisper(model, *, precision="bf16", device=0, max_sessions=64, max_batch=64, **kw):
+    """Pack a loaded reference ``Whisper`` module (whisper/model.py:335) into a WhisperEngine."""
+    from .engine import WhisperEngine
+    d = model.dims
+    dims = ModelDimensions(d.n_mels, d.n_audio_ctx, d.n_audio_state, d.n_audio_head, d.n_audio_layer,
+                           d.n_vocab, d.n_text_ctx, d.n_text_state, d.n_text_head, d.n_text_layer)
+    heads = [(int(l), int(h)) for l, h in model.alignment_heads.indices().T]      # simul_whisper.py:151-159
+    return WhisperEngine(dims, state_dict_from_torch(model.state_dict()), heads, precision=precision,
+                         device=device, max_sessions=max_sessions, max_batch=max_batch, **kw)
+
+
+def make_b200_alignatt_class():
+    """class B200AlignAtt(AlignAttHooks, AlignAttBase): the reference's template infer() over our hooks."""
+    from whisperlivekit.simul_whisper.align_att_base import AlignAttBase
+    from .alignatt import AlignAttHooks
+
+    class B200AlignAtt(AlignAttHooks, AlignAttBase):
+        pass
+
+    return B200AlignAtt
+
+
+def install(precision: str = "bf16", device: int = 0, max_sessions: int = 64, max_batch: int = 64):
+    """Route WhisperLiveKit's SimulStreaming backend through the B200 engine (call once, before
+    TranscriptionEngine is constructed)."""
+    import whisperlivekit.simul_whisper.backend as be
+    cls = make_b200_alignatt_class()
+    be.AlignAtt = cls
+    orig_load = be.SimulStreamingASR.load_model
+
+    def load_model(self, *a, **k):
+        torch_model = orig_load(self, *a, **k)
+        eng = engine_from_torch_whisper(torch_model, precision=precision, device=device,
+                                        max_sessions=max_sessions, max_batch=max_batch)
+        return B200WhisperModel(eng)
+
+    be.SimulStreamingASR.load_model = load_model
+    return cls
