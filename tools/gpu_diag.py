@@ -242,13 +242,14 @@ CHECKS = {
 
 
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] in CHECKS:
-        CHECKS[sys.argv[1]]()
+    if len(sys.argv) == 3 and sys.argv[1] == "--one" and sys.argv[2] in CHECKS:
+        CHECKS[sys.argv[2]]()
         return
-    for name in CHECKS:
+    names = [a for a in sys.argv[1:] if a in CHECKS] or list(CHECKS)
+    for name in names:
         t0 = time.time()
         try:
-            p = subprocess.run([sys.executable, os.path.abspath(__file__), name], timeout=600,
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", name], timeout=600,
                                capture_output=True, text=True)
             tail = (p.stdout[-3000:] if p.returncode else "") + p.stderr[-3000:]
             emit(check="_run", name=name, rc=p.returncode, seconds=time.time() - t0, tail=tail if p.returncode else "")

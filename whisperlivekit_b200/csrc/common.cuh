@@ -211,6 +211,73 @@ __device__ __forceinline__ void epi_store8(const Epilogue& e, int m, int n0, con
         }
     }
 }
+
+// ---------------------------------------------------------------------------------
+// Factored destination addressing for the tcgen05 GEMM epilogue:
+//   address(m, n) = rowptr(m, variant) + colterm(n) * elem_size,  variant chosen per 32-column chunk.
+// rowptr is computed once per tile and row (it hides the per-batch base pointer and every div/mod on m),
+// colterm once per chunk and lane, so the per-element work is an add.
+// ---------------------------------------------------------------------------------
+struct EpiRow {
+    char* ptr0;           // destination row base for variant 0 (nullptr: row is not stored)
+    char* ptr1;           // variant 1 (EPI_SELF_QKV k/v planes); unused otherwise
+    const float* res;     // residual row (already offset to column 0) or nullptr
+};
+
+__device__ __forceinline__ EpiRow epi_row(const Epilogue& e, int m, int M) {
+    EpiRow r{nullptr, nullptr, nullptr};
+    if (m >= M) return r;
+    const int es = (e.c_type == DT_F32) ? 4 : 2;
+    switch (e.mode) {
+        default:
+        case EPI_PLAIN:
+            r.ptr0 = reinterpret_cast<char*>(e.C) + (int64_t)m * e.ldc * es;
+            if (e.residual) r.res = e.residual + (int64_t)m * e.ldr;
+            break;
+        case EPI_ROWPTR: {
+            int b = m / e.rows_per_batch, rr = m - b * e.rows_per_batch;
+            if (rr < e.rows_valid) {
+                r.ptr0 = reinterpret_cast<char*>(e.batch_ptrs[b]) + (int64_t)rr * e.ldc * es;
+                if (e.residual) r.res = e.residual + (int64_t)rr * e.ldr;
+            }
+            break;
+        }
+        case EPI_XKV: {
+            int b = m / e.rows_per_batch, rr = m - b * e.rows_per_batch;
+            r.ptr0 = reinterpret_cast<char*>(e.batch_ptrs[b]) + (int64_t)rr * 64 * es;
+            break;
+        }
+        case EPI_SELF_QKV:
+            r.ptr0 = reinterpret_cast<char*>(e.C) + (int64_t)m * e.ldc * es;
+            r.ptr1 = reinterpret_cast<char*>(e.batch_ptrs[e.row_slot[m]]) + (int64_t)e.row_pos[m] * 64 * es;
+            break;
+    }
+    return r;
+}
+
+// element offset of column n (and which row-pointer variant its chunk uses)
+__device__ __forceinline__ int64_t epi_col(const Epilogue& e, int n, int* variant) {
+    *variant = 0;
+    switch (e.mode) {
+        default:
+        case EPI_PLAIN:
+        case EPI_ROWPTR:
+            return n;
+        case EPI_XKV: {
+            int two_d = 2 * e.d_model;
+            int l = n / two_d, rem = n - l * two_d;
+            int kv = rem / e.d_model, c = rem - kv * e.d_model;
+            return (((int64_t)l * 2 + kv) * e.n_head + (c >> 6)) * e.kv_len * 64 + (c & 63);
+        }
+        case EPI_SELF_QKV: {
+            int part = n / e.d_model, c = n - part * e.d_model;
+            if (part == 0) return c;
+            *variant = 1;
+            return (((int64_t)e.layer * 2 + (part - 1)) * e.n_head + (c >> 6)) * e.kv_len * 64 + (c & 63);
+        }
+    }
+}
+
 #endif  // __CUDACC__
 
 }  // namespace wlk

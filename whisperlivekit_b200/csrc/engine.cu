@@ -674,7 +674,8 @@ void create_engine(const wlk_dims* dims, const wlk_config* cfg, wlk_engine** out
     e->act = cfg->precision == WLK_PREC_BF16 ? DT_BF16 : DT_F32;
     e->gemm_backend = cfg->gemm_backend != WLK_BACKEND_AUTO ? cfg->gemm_backend
                       : (e->act == DT_BF16 ? WLK_BACKEND_TCGEN05 : WLK_BACKEND_SIMT);
-    e->attn_backend = cfg->attn_backend != WLK_BACKEND_AUTO ? cfg->attn_backend : WLK_BACKEND_SIMT;
+    e->attn_backend = cfg->attn_backend != WLK_BACKEND_AUTO ? cfg->attn_backend
+                      : (e->act == DT_BF16 ? WLK_BACKEND_TCGEN05 : WLK_BACKEND_SIMT);
     if (e->act != DT_BF16) { e->gemm_backend = WLK_BACKEND_SIMT; e->attn_backend = WLK_BACKEND_SIMT; }
     CUDA_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     for (auto& t : e->timers) CUDA_CHECK(cudaEventCreate(&t));

@@ -5,7 +5,7 @@
 //                               128B-swizzled, into a STAGES-deep shared-memory ring (mbarrier full/empty)
 //   warp 1      MMA issuer    : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN,
 //                               K=16) x4 per slab; accumulators live in TMEM, double-buffered (2 x BN cols)
-//   warps 2..5  epilogue      : tcgen05.ld the finished accumulator (lane = row), fused bias / GELU /
+//   warps 2..9  epilogue      : tcgen05.ld the finished accumulator (lane = row), fused bias / GELU /
 //                               column scale / fp32 residual, then bf16 or fp32 stores (plain or scattered
 //                               into the head-major KV layouts), overlapping the next tile's MMAs.
 // Tiles are walked m-fastest so the CTAs of a wave share one W panel (L2-resident) while A streams.
@@ -51,15 +51,19 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // TMA warp, MMA warp, 8 epilogue warps
+constexpr int STG_PITCH = 17;
 
 template <int BN, int STAGES>
 struct SmemLayout {
     static constexpr uint32_t A_BYTES = BM * BK * 2;
     static constexpr uint32_t B_BYTES = BN * BK * 2;
     static constexpr uint32_t STG_OFF = STAGES * (A_BYTES + B_BYTES);     // epilogue transpose staging
-    static constexpr uint32_t STG_BYTES = 4 * 32 * 33 * 4;                // 4 warps x [32][33] fp32
-    static constexpr uint32_t BAR_OFF = STG_OFF + STG_BYTES;
+    static constexpr uint32_t STG_BYTES = NUM_EPI_WARPS * 32 * STG_PITCH * 4;   // per warp [32 rows][16 cols (+1)] fp32
+    static constexpr uint32_t ROW_OFF = STG_OFF + STG_BYTES;                     // per warp EpiRow[32]
+    static constexpr uint32_t ROW_BYTES = NUM_EPI_WARPS * 32 * 24;
+    static constexpr uint32_t BAR_OFF = ROW_OFF + ROW_BYTES;
     static constexpr uint32_t TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
     static constexpr uint32_t DYN = TOTAL + 1024;   // slack for manual 1024-byte alignment
 };
@@ -97,7 +101,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(bar_tfull + 8 * i, 1);
-            ptx::mbar_init(bar_tempty + 8 * i, 128);
+            ptx::mbar_init(bar_tempty + 8 * i, 32 * NUM_EPI_WARPS);
         }
         ptx::fence_barrier_init();
     }
@@ -153,33 +157,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        // tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns at a time).  Storing
-        // that directly makes every warp store touch 32 different rows; instead each warp transposes its
-        // 32x32 block through a private padded smem tile so that lanes walk consecutive COLUMNS of one row:
-        // 64-128 B contiguous per warp instruction for every epilogue mode (plain, residual, KV scatter).
+        // ===================== epilogue (warps 2..9) =====================
+        // Two warps per TMEM lane quadrant, each owning half of the tile's columns.  tcgen05.ld hands a
+        // thread one accumulator ROW (16 columns at a time); the warp transposes that 32x16 block through
+        // a private padded smem tile so that lanes walk consecutive COLUMNS: every global access (output
+        // row, fp32 residual row, scattered KV row) is a contiguous 32-64 B run per half-warp, the bias /
+        // scale of a column live in registers, and all div/mod addressing is hoisted to once per row per
+        // tile (EpiRow) and once per chunk (epi_col).
+        const int ew = warp - 2;
         const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-        float* stg = reinterpret_cast<float*>(smem_gen + L::STG_OFF) + q * (32 * 33);
+        const int hc = ew >> 2;                       // which half of the tile's columns
+        float* stg = reinterpret_cast<float*>(smem_gen + L::STG_OFF) + ew * (32 * STG_PITCH);
+        EpiRow* rowinfo = reinterpret_cast<EpiRow*>(smem_gen + L::ROW_OFF) + ew * 32;
+        const int rsel = lane >> 4, col = lane & 15;
+        const int es = (epi.c_type == DT_F32) ? 4 : 2;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m_blk = tile % num_m, n_blk = tile / num_m;
             const uint32_t as = it & 1, ap = (it >> 1) & 1;
+            const int row_base = m_blk * BM + q * 32;
+            rowinfo[lane] = epi_row(epi, row_base + lane, M);
+            __syncwarp();
             ptx::mbar_wait(bar_tfull + 8 * as, ap);
             ptx::tc_fence_after();
-            const int row_base = m_blk * BM + q * 32;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, r);
+                const int c0 = hc * (BN / 2) + c * 16;            // first column of this chunk inside the tile
+                uint32_t r[16];
+                ptx::tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c0, r);
                 ptx::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+                for (int j = 0; j < 16; ++j) stg[lane * STG_PITCH + j] = __uint_as_float(r[j]);
                 __syncwarp();
-                const int n = n_blk * BN + c * 32 + lane;
+                const int n = n_blk * BN + c0 + col;
                 if (n < N) {
-                    const int rows = min(32, M - row_base);
+                    int variant;
+                    const int64_t coff = epi_col(epi, n, &variant) * es;
+                    const float bias_v = epi.bias ? __ldg(epi.bias + n) : 0.f;
+                    const bool scaled = (epi.scale_period ? (n % epi.scale_period) : n) < epi.scale_cols;
+                    const float scale_v = scaled ? epi.col_scale : 1.f;
 #pragma unroll 4
-                    for (int i = 0; i < rows; ++i) epi_store1(epi, row_base + i, n, stg[i * 33 + lane]);
+                    for (int i2 = 0; i2 < 16; ++i2) {
+                        const int i = 2 * i2 + rsel;
+                        const EpiRow ri = rowinfo[i];
+                        char* p = variant ? ri.ptr1 : ri.ptr0;
+                        if (p == nullptr) continue;
+                        float v = stg[i * STG_PITCH + col] + bias_v;
+                        if (epi.gelu) v = gelu_erf(v);
+                        v *= scale_v;
+                        if (ri.res) v += ri.res[n];
+                        if (es == 4) *reinterpret_cast<float*>(p + coff) = v;
+                        else *reinterpret_cast<bf16*>(p + coff) = __float2bfloat16_rn(v);
+                    }
                 }
                 __syncwarp();
             }

@@ -442,17 +442,42 @@ void dec_self_attention(const void* q, int type, const DecJob* jobs, int n_jobs,
 //    simul_whisper.py:401-416)
 //   grid (H, jobs), 256 threads, 8 queries per pass
 // =====================================================================================
+template <typename T> struct RowVec;          // 16-byte slice of a 64-wide K/V row held by one lane
+template <> struct RowVec<bf16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void load(const bf16* p, float* o) {
+        uint4 u = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { o[2 * i] = __low2float(h[i]); o[2 * i + 1] = __high2float(h[i]); }
+    }
+};
+template <> struct RowVec<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void load(const float* p, float* o) {
+        float4 v = *reinterpret_cast<const float4*>(p);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+};
+
+// K and V planes are streamed exactly once per block of QB queries with 128-bit loads: a group of LPK lanes
+// covers one 64-wide row, so a warp instruction reads KPW whole rows (512 contiguous bytes).
 template <typename T>
 __global__ void __launch_bounds__(256)
 dec_cross_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, int layer, int n_head, int d_model,
                       int n_text_ctx, const int32_t* __restrict__ align_rank, T* __restrict__ out) {
     constexpr int QB = 8;
+    constexpr int VN = RowVec<T>::N;          // elements per lane
+    constexpr int LPK = 64 / VN;              // lanes per key row  (8 bf16 / 16 fp32)
+    constexpr int KPW = 32 / LPK;             // key rows per warp instruction (4 / 2)
     extern __shared__ float sm[];
     float* sc = sm;                          // [QB][1500]
     float* qs = sc + QB * N_CTX;             // [QB][64]
-    float* part = qs + QB * 64;              // [4][QB][64]
+    float* part = qs + QB * 64;              // [8 warps][QB][64]
     const DecJob job = jobs[blockIdx.y];
     const int h = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = lane / LPK;              // which of the KPW rows of this warp instruction
+    const int seg = (lane % LPK) * VN;       // first of this lane's VN dims
     const T* Kc = reinterpret_cast<const T*>(job.cross_kv) + (((int64_t)layer * 2 + 0) * n_head + h) * N_CTX * 64;
     const T* Vc = reinterpret_cast<const T*>(job.cross_kv) + (((int64_t)layer * 2 + 1) * n_head + h) * N_CTX * 64;
     const int rank = align_rank[layer * n_head + h];
@@ -463,22 +488,39 @@ dec_cross_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, 
             qs[i] = (qi < nq) ? to_f32(q[(int64_t)(job.row_off + t0 + qi) * d_model + h * 64 + e]) : 0.f;
         }
         __syncthreads();
-        for (int key = tid; key < N_CTX; key += 256) {
-            const T* kr = Kc + (int64_t)key * 64;
-            float s[QB];
+        // ---- scores: s[qi][key] = q[qi] . K[key]
+        {
+            float qr[QB][VN];
 #pragma unroll
-            for (int qi = 0; qi < QB; ++qi) s[qi] = 0.f;
-#pragma unroll 8
-            for (int e = 0; e < 64; ++e) {
-                float kv = to_f32(kr[e]);
+            for (int qi = 0; qi < QB; ++qi)
 #pragma unroll
-                for (int qi = 0; qi < QB; ++qi) s[qi] = fmaf(qs[qi * 64 + e], kv, s[qi]);
+                for (int j = 0; j < VN; ++j) qr[qi][j] = qs[qi * 64 + seg + j];
+            for (int k0 = warp * KPW; k0 < N_CTX; k0 += 8 * KPW) {
+                const int key = k0 + sub;
+                float kv[VN];
+                if (key < N_CTX) RowVec<T>::load(Kc + (int64_t)key * 64 + seg, kv);
+                else {
+#pragma unroll
+                    for (int j = 0; j < VN; ++j) kv[j] = 0.f;
+                }
+                float s[QB];
+#pragma unroll
+                for (int qi = 0; qi < QB; ++qi) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int j = 0; j < VN; ++j) a = fmaf(qr[qi][j], kv[j], a);
+#pragma unroll
+                    for (int o = LPK / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                    s[qi] = a;
+                }
+                if ((lane % LPK) == 0 && key < N_CTX) {
+#pragma unroll
+                    for (int qi = 0; qi < QB; ++qi) sc[qi * N_CTX + key] = s[qi];
+                }
             }
-#pragma unroll
-            for (int qi = 0; qi < QB; ++qi) sc[qi * N_CTX + key] = s[qi];
         }
         __syncthreads();
-        // softmax: warp w normalises query row w (QB == number of warps)
+        // ---- softmax: warp w normalises query row w; alignment heads export the probabilities
         if (warp < nq) {
             float* r = sc + warp * N_CTX;
             float mx = -INFINITY;
@@ -497,24 +539,49 @@ dec_cross_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, 
             }
         }
         __syncthreads();
+        // ---- out[qi][e] = sum_key p[qi][key] V[key][e]
         {
-            const int g = tid >> 6, e = tid & 63;
-            float acc[QB];
+            float acc[QB][VN];
 #pragma unroll
-            for (int qi = 0; qi < QB; ++qi) acc[qi] = 0.f;
-            for (int key = g; key < N_CTX; key += 4) {
-                float v = to_f32(Vc[(int64_t)key * 64 + e]);
+            for (int qi = 0; qi < QB; ++qi)
 #pragma unroll
-                for (int qi = 0; qi < QB; ++qi) acc[qi] = fmaf(sc[qi * N_CTX + key], v, acc[qi]);
+                for (int j = 0; j < VN; ++j) acc[qi][j] = 0.f;
+            for (int k0 = warp * KPW; k0 < N_CTX; k0 += 8 * KPW) {
+                const int key = k0 + sub;
+                if (key < N_CTX) {
+                    float vv[VN];
+                    RowVec<T>::load(Vc + (int64_t)key * 64 + seg, vv);
+#pragma unroll
+                    for (int qi = 0; qi < QB; ++qi) {
+                        const float p = sc[qi * N_CTX + key];
+#pragma unroll
+                        for (int j = 0; j < VN; ++j) acc[qi][j] = fmaf(p, vv[j], acc[qi][j]);
+                    }
+                }
             }
+            // fold the KPW row-groups of the warp, then the 8 warps through shared memory
 #pragma unroll
-            for (int qi = 0; qi < QB; ++qi) part[(g * QB + qi) * 64 + e] = acc[qi];
+            for (int qi = 0; qi < QB; ++qi)
+#pragma unroll
+                for (int j = 0; j < VN; ++j) {
+                    float a = acc[qi][j];
+#pragma unroll
+                    for (int o = LPK; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                    acc[qi][j] = a;
+                }
+            if (sub == 0) {
+#pragma unroll
+                for (int qi = 0; qi < QB; ++qi)
+#pragma unroll
+                    for (int j = 0; j < VN; ++j) part[(warp * QB + qi) * 64 + seg + j] = acc[qi][j];
+            }
         }
         __syncthreads();
         for (int i = tid; i < nq * 64; i += 256) {
             int qi = i >> 6, e = i & 63;
-            float v = part[(0 * QB + qi) * 64 + e] + part[(1 * QB + qi) * 64 + e] + part[(2 * QB + qi) * 64 + e] +
-                      part[(3 * QB + qi) * 64 + e];
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) v += part[(w * QB + qi) * 64 + e];
             out[(int64_t)(job.row_off + t0 + qi) * d_model + h * 64 + e] = from_f32<T>(v);
         }
         __syncthreads();
@@ -523,7 +590,7 @@ dec_cross_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, 
 void dec_cross_attention(const void* q, int type, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model,
                          int n_text_ctx, const int32_t* align_rank, void* out, cudaStream_t st) {
     dim3 grid(n_head, n_jobs);
-    const int smem = (8 * N_CTX + 8 * 64 + 4 * 8 * 64) * 4;
+    const int smem = (8 * N_CTX + 8 * 64 + 8 * 8 * 64) * 4;
     static bool set = false;
     if (!set) {
         CUDA_CHECK(cudaFuncSetAttribute(dec_cross_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
