@@ -165,6 +165,7 @@ def main():
     import torch
     import torch.distributed as dist
     from whisperlivekit_b200.engine import WhisperEngine
+    from whisperlivekit_b200.sharding import broadcast_blob
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -180,7 +181,7 @@ def main():
         class _Blob:
             __cuda_array_interface__ = dict(shape=(nbytes,), typestr="|u1", data=(ptr, False), version=2)
         blob = torch.as_tensor(_Blob(), device=f"cuda:{local_rank}")
-        dist.broadcast(blob, src=0)
+        broadcast_blob(blob, src=0)
         torch.cuda.synchronize()
         if rank != 0:
             eng.adopt_weights()
@@ -236,12 +237,29 @@ def main():
             dist.barrier()
         return ms, prof
 
+    if os.environ.get("WLK_NCU"):
+        # profiler capture mode: warm up, then exactly one step between cudaProfilerStart/Stop
+        # (ncu --profile-from-start off ...).  Numbers printed under a profiler are never bench values.
+        for k in range(args.warmup):
+            step(False, k)
+        eng.sync()
+        torch.cuda.profiler.start()
+        step(False, 0)
+        eng.sync()
+        torch.cuda.profiler.stop()
+        print(json.dumps(dict(ncu_capture=True, streams=B)))
+        return
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_dev, prof = timed(False, args.steps, args.warmup, True)
+    ms_dev, _ = timed(False, args.steps, args.warmup, False)
     clocks = sampler.summary() if sampler else None
     ms_e2e, _ = timed(True, args.steps, max(1, args.warmup // 3), False)
+    # same steps once more with a CUDA-event pair around every kernel class launch (engine stream):
+    # per-class device time for the roofline; kept out of `value` because ~10^4 event records per step
+    # cost a few percent of host-side launch throughput.
+    ms_prof, prof = timed(False, args.steps, 0, True)
 
     if rank == 0:
         peaks = load_peaks()
@@ -271,6 +289,7 @@ def main():
                           peak_source=peaks["source"],
                           flops_per_launch=g["flops"] / max(1, g["launches"]), ms_per_launch=g["ms"] / max(1, g["launches"])),
             kernel_classes=classes,
+            profiled_ms_per_step=ms_prof / args.steps,
         )
         if not args.no_cpu_baseline:
             sd_cpu = sd if world == 1 or rank == 0 else None

@@ -113,7 +113,10 @@ int wlk_read_logits(wlk_engine* e, int32_t sid, int32_t which /* 0 last, 1 sot r
 int wlk_read_align_attn(wlk_engine* e, int32_t sid, float* out, int64_t capacity, int32_t* rows, int32_t* cols);
 
 /* ---- op-level entry points (kernel tests, roofline benches). Device pointers.
- *      a_type/w_type/c_type: 0 = fp32, 1 = bf16.  C[M,N] = act(A[M,K] W[N,K]^T + bias)      */
+ *      backend: WLK_BACKEND_SIMT, WLK_BACKEND_TCGEN05 (auto tile choice), 3 = force the one-CTA tcgen05 kernel,
+ *      4 = force the CTA-pair (cta_group::2) kernel.
+ *      a_type/w_type/c_type: 0 = fp32, 1 = bf16.  C[M,N] = act(A[M,K] W[N,K]^T + bias); `gelu` is a flag
+ *      word: bit 0 = erf-GELU, bit 1 = accumulate into the fp32 C in place (C += A W^T + bias).           */
 int wlk_op_gemm(wlk_engine* e, int backend, const void* A, int a_type, int64_t lda,
                 const void* W, int w_type, int64_t ldw, const float* bias,
                 void* C, int c_type, int64_t ldc, int M, int N, int K, int gelu);

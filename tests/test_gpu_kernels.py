@@ -122,3 +122,36 @@ def test_encoder_attention_tcgen05(eng, d, H, B):
     assert not torch.isnan(out.float()).any()
     assert (out.float() - ref).abs().max().item() < 2e-2
     e2.close()
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 512, 256), (1500, 1280, 1280), (3000, 384, 240),
+                                   (257, 300, 72), (24000, 1280, 1280), (4500, 5120, 1280)])
+def test_gemm_tcgen05_cta_pair(eng, M, N, K):
+    """cta_group::2 kernel (256x256 tiles over 2-CTA clusters) vs fp32 reference and vs the 1-CTA kernel."""
+    g = torch.Generator(device="cuda").manual_seed(M + 3 * N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    out = _gemm(eng, "tcgen05_pair", A, W, b, True, torch.float32)
+    ref = _ref(A, W, b, True)
+    assert not torch.isnan(out).any()
+    assert (out - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
+    one = _gemm(eng, "tcgen05_1cta", A, W, b, True, torch.float32)
+    assert (out - one).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K", [(16, 1280, 1280), (64, 1280, 5120), (1, 384, 1536), (48, 512, 512)])
+def test_gemm_tcgen05_split_k_in_place(eng, M, N, K):
+    """Decoder-shaped GEMMs updating the fp32 residual stream in place (x += A W^T + b): the short/narrow
+    case is split along K with fp32 atomics."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    x0 = torch.randn(M, N, device="cuda", generator=g)
+    x = x0.clone()
+    torch.cuda.synchronize()
+    eng.op_gemm("tcgen05", A.data_ptr(), 1, K, W.data_ptr(), 1, K, b.data_ptr(), x.data_ptr(), 0, N, M, N, K, 2)
+    eng.sync()
+    ref = x0 + A.float() @ W.float().t() + b
+    assert (x - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())

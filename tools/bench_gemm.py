@@ -10,6 +10,7 @@ from whisperlivekit_b200.engine import WhisperEngine
 M, N, K = (int(x) for x in sys.argv[1:4]) if len(sys.argv) >= 4 else (24000, 5120, 1280)
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 out_bf16 = os.environ.get("OUT", "bf16") == "bf16"
+gelu = os.environ.get("GELU", "1") == "1"
 eng = WhisperEngine(DIMS["micro"], None, [(0, 0)], precision="bf16", max_sessions=1, max_batch=1)
 A = torch.randn(M, K, device="cuda").bfloat16()
 W = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
@@ -17,10 +18,10 @@ b = torch.randn(N, device="cuda")
 C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16 if out_bf16 else torch.float32)
 torch.cuda.synchronize()
 for _ in range(2):
-    eng.op_gemm("tcgen05", A.data_ptr(), 1, K, W.data_ptr(), 1, K, b.data_ptr(), C.data_ptr(), 1 if out_bf16 else 0, N, M, N, K, True)
+    eng.op_gemm(os.environ.get("BACKEND", "tcgen05"), A.data_ptr(), 1, K, W.data_ptr(), 1, K, b.data_ptr(), C.data_ptr(), 1 if out_bf16 else 0, N, M, N, K, gelu)
 eng.timer_record(0)
 for _ in range(iters):
-    eng.op_gemm("tcgen05", A.data_ptr(), 1, K, W.data_ptr(), 1, K, b.data_ptr(), C.data_ptr(), 1 if out_bf16 else 0, N, M, N, K, True)
+    eng.op_gemm(os.environ.get("BACKEND", "tcgen05"), A.data_ptr(), 1, K, W.data_ptr(), 1, K, b.data_ptr(), C.data_ptr(), 1 if out_bf16 else 0, N, M, N, K, gelu)
 eng.timer_record(1)
 ms = eng.timer_elapsed_ms(0, 1) / iters
-print(f"gemm {M}x{N}x{K}: {ms:.3f} ms  {2.0*M*N*K/ms/1e9:.1f} TFLOP/s")
+print(f"gemm {M}x{N}x{K} gelu={int(gelu)} out={"bf16" if out_bf16 else "f32"}: {ms:.3f} ms  {2.0*M*N*K/ms/1e9:.1f} TFLOP/s")

@@ -15,6 +15,8 @@
 //                             online; final O / l stored as bf16.
 #include <cudaTypedefs.h>
 
+#include <type_traits>
+
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -32,6 +34,12 @@ constexpr uint32_t SM_Q = 0, SM_K = TILE_BYTES, SM_V = 3 * TILE_BYTES, SM_BAR = 
 constexpr uint32_t ATT_SMEM = SM_BAR + 128 + 1024;
 constexpr uint32_t TM_S = 0, TM_O = 128, TM_P = 192, TM_COLS = 256;
 constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ float fast_exp2(float x) {      // MUFU.EX2, flush-to-zero, exp2(-inf) = 0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r) {
     asm volatile(
@@ -138,11 +146,14 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, int n_head, int d_mod
 #pragma unroll
         for (int e = 0; e < DH; ++e) acc[e] = 0.f;
         float m = -INFINITY, l = 0.f;                         // running max (log2 domain) and sum
-        for (int j = 0; j < NT; ++j) {
-            const int n_valid = min(BKV, N_CTX - j * BKV);
+        // One key tile.  MASKED only for the last tile (92 valid keys of 128): the steady-state path carries
+        // no per-element predicates, exp2 is a bare MUFU.EX2 (ex2.approx.ftz) and the row sum is taken on the
+        // fp32 probabilities -- the profile of the first version was 26 issued instructions per exponential.
+        auto tile = [&](int j, auto masked_tag) {
+            constexpr bool MASKED = decltype(masked_tag)::value;
+            const int n_valid = N_CTX - j * BKV;              // only read when MASKED
             ptx::mbar_wait(bar_s_full, j & 1);
             ptx::tc_fence_after();
-            // pass 1: row max
             float mx = -INFINITY;
 #pragma unroll 1
             for (int c = 0; c < BKV / 32; ++c) {
@@ -151,12 +162,11 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, int n_head, int d_mod
                 ptx::tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                    if (c * 32 + i < n_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    if (!MASKED || c * 32 + i < n_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
             }
             const float m_new = fmaxf(m, mx * LOG2E);
-            const float alpha = exp2f(m - m_new);
-            // O_{j-1} (computed against the previous max) joins the accumulator before rescaling
-            if (j > 0) {
+            const float alpha = fast_exp2(m - m_new);
+            if (j > 0) {                                      // O_{j-1} joins the accumulator before rescaling
                 ptx::mbar_wait(bar_o_full, (j - 1) & 1);
                 ptx::tc_fence_after();
 #pragma unroll
@@ -165,12 +175,9 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, int n_head, int d_mod
                     ptx::tmem_ld_32x32(tmem + lane_addr + TM_O + c * 32, v);
                     ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[c * 32 + i] += __uint_as_float(v[i]);
+                    for (int i = 0; i < 32; ++i) acc[c * 32 + i] = (acc[c * 32 + i] + __uint_as_float(v[i])) * alpha;
                 }
             }
-#pragma unroll
-            for (int e = 0; e < DH; ++e) acc[e] *= alpha;
-            // pass 2: probabilities, row sum, pack to bf16 into the P region
             float rs = 0.f;
 #pragma unroll 1
             for (int c = 0; c < BKV / 32; ++c) {
@@ -180,11 +187,14 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, int n_head, int d_mod
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    float p0 = (c * 32 + 2 * i < n_valid) ? exp2f(fmaf(__uint_as_float(v[2 * i]), LOG2E, -m_new)) : 0.f;
-                    float p1 = (c * 32 + 2 * i + 1 < n_valid) ? exp2f(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, -m_new)) : 0.f;
+                    float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), LOG2E, -m_new));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, -m_new));
+                    if (MASKED) {
+                        if (c * 32 + 2 * i >= n_valid) p0 = 0.f;
+                        if (c * 32 + 2 * i + 1 >= n_valid) p1 = 0.f;
+                    }
+                    rs += p0 + p1;
                     __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-                    // the row sum uses the rounded values the tensor core will multiply
-                    rs += __low2float(hb) + __high2float(hb);
                     pk[i] = *reinterpret_cast<uint32_t*>(&hb);
                 }
                 tmem_st_32x16(tmem + lane_addr + TM_P + c * 16, pk);
@@ -195,7 +205,10 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, int n_head, int d_mod
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_s_free);     // S fully consumed: next Q K^T may overwrite it
             ptx::mbar_arrive(bar_p_full);     // P written, O_{j-1} read: P V may run
-        }
+        };
+#pragma unroll 1
+        for (int j = 0; j < NT - 1; ++j) tile(j, std::false_type{});
+        tile(NT - 1, std::true_type{});
         ptx::mbar_wait(bar_o_full, (NT - 1) & 1);
         ptx::tc_fence_after();
 #pragma unroll

@@ -87,7 +87,8 @@ struct GemmArgs {
 };
 
 void gemm_simt(const GemmArgs& g, cudaStream_t st);
-void gemm_tcgen05(const GemmArgs& g, cudaStream_t st, int num_sms);
+void gemm_tcgen05(const GemmArgs& g, cudaStream_t st, int num_sms, int variant = 0);   // 0 auto, 1 one-CTA, 2 CTA pair
+void gemm_tcgen05_pair(const GemmArgs& g, cudaStream_t st, int num_sms);
 bool gemm_tcgen05_supported(const GemmArgs& g, std::string* why);
 
 // ---------------------------------------------------------------------------------

@@ -520,13 +520,14 @@ void decode_batch(wlk_engine* e, const int32_t* sids, int n, const int32_t* toke
     int32_t* sel = sg.host<int32_t>(2 * n, &sel_dev);
     void** skv_dev; void** skv = sg.host<void*>(n, &skv_dev);
     void** lptr_dev; void** lptr = sg.host<void*>(2 * n, &lptr_dev);
-    int n_sel = 0, r = 0;
+    int n_sel = 0, r = 0, max_tq = 0;
     for (int i = 0; i < n; ++i) {
         Session& s = get_session(e, sids[i]);
         for (int j = 0; j < i; ++j) WLK_CHECK(sids[j] != sids[i], "session %d appears twice in the batch", sids[i]);
         WLK_CHECK(s.encoded, "session %d: decode before encode", sids[i]);
         const int tq = offsets[i + 1] - offsets[i];
         WLK_CHECK(tq >= 1, "session %d: empty token list", sids[i]);
+        if (tq > max_tq) max_tq = tq;
         WLK_CHECK(s.self_len + tq <= ctx, "session %d: %d + %d tokens exceed n_text_ctx %d", sids[i], s.self_len, tq, ctx);
         const bool first = s.iter_row_start.empty();
         if (first) WLK_CHECK(sot_index >= 0 && sot_index < tq, "sot_index %d outside the %d fed tokens", sot_index, tq);
@@ -575,7 +576,7 @@ void decode_batch(wlk_engine* e, const int32_t* sids, int n, const int32_t* toke
             g.epi.C = e->dq; g.epi.c_type = e->act; g.epi.ldc = dt;
             run_gemm(e, g, WLK_KC_GEMM_DEC); }
         {   ProfScope ps(e, WLK_KC_ATTN_DEC_CROSS, 0, (double)n * 2 * H * N_CTX * 64 * es);
-            dec_cross_attention(e->dq, e->act, dj_dev, n, li, H, dt, ctx, e->align_rank_dev, e->datt, e->st); }
+            dec_cross_attention(e->dq, e->act, dj_dev, n, li, H, dt, ctx, e->align_rank_dev, e->datt, max_tq, e->st); }
         {   GemmArgs g;
             g.A = e->datt; g.a_type = e->act; g.lda = dt; g.W = L.Woc; g.w_type = e->act; g.ldw = dt;
             g.M = R; g.N = dt; g.K = dt;
@@ -1117,9 +1118,12 @@ int wlk_op_gemm(wlk_engine* e, int backend, const void* A, int a_type, int64_t l
     LOCK(e);
     GemmArgs g;
     g.A = A; g.a_type = a_type; g.lda = lda; g.W = Wm; g.w_type = w_type; g.ldw = ldw; g.M = M; g.N = N; g.K = K;
-    g.epi.bias = bias; g.epi.gelu = gelu; g.epi.C = C; g.epi.c_type = c_type; g.epi.ldc = ldc;
+    g.epi.bias = bias; g.epi.gelu = gelu & 1; g.epi.C = C; g.epi.c_type = c_type; g.epi.ldc = ldc;
+    if (gelu & 2) { WLK_CHECK(c_type == DT_F32, "in-place accumulation needs an fp32 output"); g.epi.residual = (const float*)C; g.epi.ldr = ldc; }
     ProfScope ps(e, WLK_KC_MISC, 2.0 * M * (double)N * K, 0);
-    if (backend == WLK_BACKEND_TCGEN05) gemm_tcgen05(g, e->st, e->num_sms);
+    if (backend == WLK_BACKEND_TCGEN05) gemm_tcgen05(g, e->st, e->num_sms, 0);
+    else if (backend == 3) gemm_tcgen05(g, e->st, e->num_sms, 1);
+    else if (backend == 4) gemm_tcgen05(g, e->st, e->num_sms, 2);
     else gemm_simt(g, e->st);
     WLK_API_END
 }

@@ -11,8 +11,9 @@
 // Tiles are walked m-fastest so the CTAs of a wave share one W panel (L2-resident) while A streams.
 #include <cudaTypedefs.h>
 
-#include "common.cuh"
-#include "ptx.cuh"
+#include <cstdlib>
+
+#include "gemm_epi.cuh"
 
 namespace wlk {
 
@@ -53,17 +54,15 @@ constexpr int BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;   // TMA warp, MMA warp, 8 epilogue warps
-constexpr int STG_PITCH = 17;
+
 
 template <int BN, int STAGES>
 struct SmemLayout {
     static constexpr uint32_t A_BYTES = BM * BK * 2;
     static constexpr uint32_t B_BYTES = BN * BK * 2;
     static constexpr uint32_t STG_OFF = STAGES * (A_BYTES + B_BYTES);     // epilogue transpose staging
-    static constexpr uint32_t STG_BYTES = NUM_EPI_WARPS * 32 * STG_PITCH * 4;   // per warp [32 rows][16 cols (+1)] fp32
-    static constexpr uint32_t ROW_OFF = STG_OFF + STG_BYTES;                     // per warp EpiRow[32]
-    static constexpr uint32_t ROW_BYTES = NUM_EPI_WARPS * 32 * 24;
-    static constexpr uint32_t BAR_OFF = ROW_OFF + ROW_BYTES;
+    static constexpr uint32_t STG_BYTES = NUM_EPI_WARPS * EPI_BIAS_FLOATS * 4;   // per-warp bias scratch
+    static constexpr uint32_t BAR_OFF = STG_OFF + STG_BYTES;
     static constexpr uint32_t TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
     static constexpr uint32_t DYN = TOTAL + 1024;   // slack for manual 1024-byte alignment
 };
@@ -71,7 +70,7 @@ struct SmemLayout {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M, int N, int K,
-               Epilogue epi) {
+               int splits, Epilogue epi) {
     using L = SmemLayout<BN, STAGES>;
     constexpr uint32_t TMEM_COLS = 2 * BN;           // 128 / 256 / 512: powers of two >= 32
     extern __shared__ uint8_t smem_raw[];
@@ -89,8 +88,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
-    const int num_tiles = num_m * num_n;
-    const int num_k = (K + BK - 1) / BK;
+    const int num_mn = num_m * num_n;
+    const int num_tiles = num_mn * splits;            // split-K: a work item is (k-range, n block, m block)
+    const int num_k_total = (K + BK - 1) / BK;
+    const int kb_per_split = (num_k_total + splits - 1) / splits;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
@@ -119,8 +120,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile % num_m, n_blk = tile / num_m;
-                for (int kb = 0; kb < num_k; ++kb) {
+                const int sp = tile / num_mn, mn = tile - sp * num_mn;
+                const int m_blk = mn % num_m, n_blk = mn / num_m;
+                const int kb_end = min(num_k_total, (sp + 1) * kb_per_split);
+                for (int kb = sp * kb_per_split; kb < kb_end; ++kb) {
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, L::A_BYTES + L::B_BYTES);
                     ptx::tma_load_2d(sA + stage * L::A_BYTES, &tmA, bar_full + 8 * stage, kb * BK, m_blk * BM);
@@ -137,7 +140,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t as = it & 1, ap = (it >> 1) & 1;
             ptx::mbar_wait(bar_tempty + 8 * as, ap ^ 1);
             ptx::tc_fence_after();
-            for (int kb = 0; kb < num_k; ++kb) {
+            const int sp = tile / num_mn;
+            const int kb_begin = sp * kb_per_split, kb_end = min(num_k_total, (sp + 1) * kb_per_split);
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
                 ptx::mbar_wait(bar_full + 8 * stage, phase);
                 ptx::tc_fence_after();
                 if (lane == 0) {
@@ -147,10 +152,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advancing K by 16 bf16 = 32 bytes = +2 in the (addr >> 4) field
                         ptx::umma_bf16_ss(tmem_base + as * BN, da + 2 * k, db + 2 * k, idesc,
-                                          (kb > 0 || k > 0) ? 1u : 0u);
+                                          (kb > kb_begin || k > 0) ? 1u : 0u);
                     }
                     ptx::umma_commit(bar_empty + 8 * stage);              // frees the smem slot when MMAs retire
-                    if (kb == num_k - 1) ptx::umma_commit(bar_tfull + 8 * as);   // accumulator ready
+                    if (kb == kb_end - 1) ptx::umma_commit(bar_tfull + 8 * as);  // accumulator ready
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -158,60 +163,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ===================== epilogue (warps 2..9) =====================
-        // Two warps per TMEM lane quadrant, each owning half of the tile's columns.  tcgen05.ld hands a
-        // thread one accumulator ROW (16 columns at a time); the warp transposes that 32x16 block through
-        // a private padded smem tile so that lanes walk consecutive COLUMNS: every global access (output
-        // row, fp32 residual row, scattered KV row) is a contiguous 32-64 B run per half-warp, the bias /
-        // scale of a column live in registers, and all div/mod addressing is hoisted to once per row per
-        // tile (EpiRow) and once per chunk (epi_col).
+        // Two warps per TMEM lane quadrant, each owning half of the tile's columns (see gemm_epi.cuh).
         const int ew = warp - 2;
         const int q = warp & 3;                       // TMEM lane quadrant this warp may access
         const int hc = ew >> 2;                       // which half of the tile's columns
-        float* stg = reinterpret_cast<float*>(smem_gen + L::STG_OFF) + ew * (32 * STG_PITCH);
-        EpiRow* rowinfo = reinterpret_cast<EpiRow*>(smem_gen + L::ROW_OFF) + ew * 32;
-        const int rsel = lane >> 4, col = lane & 15;
-        const int es = (epi.c_type == DT_F32) ? 4 : 2;
+        float* sbias = reinterpret_cast<float*>(smem_gen + L::STG_OFF) + ew * EPI_BIAS_FLOATS;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m_blk = tile % num_m, n_blk = tile / num_m;
+            const int sp = tile / num_mn, mn = tile - sp * num_mn;
+            const int m_blk = mn % num_m, n_blk = mn / num_m;
             const uint32_t as = it & 1, ap = (it >> 1) & 1;
-            const int row_base = m_blk * BM + q * 32;
-            rowinfo[lane] = epi_row(epi, row_base + lane, M);
-            __syncwarp();
+            const EpiRow row = epi_row(epi, m_blk * BM + q * 32 + lane, M);
             ptx::mbar_wait(bar_tfull + 8 * as, ap);
             ptx::tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                const int c0 = hc * (BN / 2) + c * 16;            // first column of this chunk inside the tile
-                uint32_t r[16];
-                ptx::tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c0, r);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) stg[lane * STG_PITCH + j] = __uint_as_float(r[j]);
-                __syncwarp();
-                const int n = n_blk * BN + c0 + col;
-                if (n < N) {
-                    int variant;
-                    const int64_t coff = epi_col(epi, n, &variant) * es;
-                    const float bias_v = epi.bias ? __ldg(epi.bias + n) : 0.f;
-                    const bool scaled = (epi.scale_period ? (n % epi.scale_period) : n) < epi.scale_cols;
-                    const float scale_v = scaled ? epi.col_scale : 1.f;
-#pragma unroll 4
-                    for (int i2 = 0; i2 < 16; ++i2) {
-                        const int i = 2 * i2 + rsel;
-                        const EpiRow ri = rowinfo[i];
-                        char* p = variant ? ri.ptr1 : ri.ptr0;
-                        if (p == nullptr) continue;
-                        float v = stg[i * STG_PITCH + col] + bias_v;
-                        if (epi.gelu) v = gelu_erf(v);
-                        v *= scale_v;
-                        if (ri.res) v += ri.res[n];
-                        if (es == 4) *reinterpret_cast<float*>(p + coff) = v;
-                        else *reinterpret_cast<bf16*>(p + coff) = __float2bfloat16_rn(v);
-                    }
-                }
-                __syncwarp();
-            }
+            epilogue_warp_tile(epi, sbias, row, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN,
+                               n_blk * BN, hc * (BN / 2), BN / 32, N, lane, splits > 1, sp == 0);
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_tempty + 8 * as);
         }
@@ -223,7 +189,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int BN, int STAGES>
-void launch(const GemmArgs& g, cudaStream_t st, int num_sms) {
+void launch(const GemmArgs& g, cudaStream_t st, int num_sms, int splits = 1) {
     using L = SmemLayout<BN, STAGES>;
     CUtensorMap tmA, tmW;
     std::string err;
@@ -235,9 +201,9 @@ void launch(const GemmArgs& g, cudaStream_t st, int num_sms) {
                                         (int)L::DYN));
         attr_set = true;
     }
-    const int num_tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+    const int num_tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * splits;
     const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-    gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, L::DYN, st>>>(tmA, tmW, g.M, g.N, g.K, g.epi);
+    gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, L::DYN, st>>>(tmA, tmW, g.M, g.N, g.K, splits, g.epi);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -253,15 +219,41 @@ bool gemm_tcgen05_supported(const GemmArgs& g, std::string* why) {
     return true;
 }
 
-void gemm_tcgen05(const GemmArgs& g, cudaStream_t st, int num_sms) {
+void gemm_tcgen05(const GemmArgs& g, cudaStream_t st, int num_sms, int variant) {
     std::string why;
     WLK_CHECK(gemm_tcgen05_supported(g, &why), "gemm_tcgen05: %s", why.c_str());
-    // BN=256 keeps the tensor pipe busiest per smem byte; narrow outputs use smaller tiles so the
-    // grid still covers the SMs.
+    static const int forced = [] { const char* v = getenv("WLK_GEMM_VARIANT"); return v ? atoi(v) : 0; }();
+    if (variant == 0) variant = forced;
+    // Large problems go to the CTA-pair kernel (256x256 tiles, half the operand traffic per MAC); the
+    // one-CTA kernel serves narrow or short problems with smaller tiles so the grid still covers the SMs.
+    const int tiles_pair = ((g.M + 255) / 256) * ((g.N + 255) / 256);
+    if (variant == 2 || (variant == 0 && g.N >= 256 && g.M >= 256 && tiles_pair >= num_sms / 2)) {
+        gemm_tcgen05_pair(g, st, num_sms);
+        return;
+    }
     const int tiles256 = ((g.M + BM - 1) / BM) * ((g.N + 255) / 256);
     if (g.N >= 256 && tiles256 >= num_sms) launch<256, 4>(g, st, num_sms);
     else if (g.N >= 128 && ((g.M + BM - 1) / BM) * ((g.N + 127) / 128) >= num_sms / 2) launch<128, 6>(g, st, num_sms);
-    else launch<64, 8>(g, st, num_sms);
+    else {
+        // Short, narrow problems (the decoder's per-token GEMMs) cannot fill the GPU with output tiles alone.
+        // When the output is the fp32 residual stream updated in place (x += A W^T + b), the K range is split
+        // across CTAs that accumulate with fp32 atomics (the first split carries the bias).
+        int splits = 1;
+        const int tiles = ((g.M + BM - 1) / BM) * ((g.N + 63) / 64);
+        const bool in_place = g.epi.mode == EPI_PLAIN && g.epi.c_type == DT_F32 && g.epi.residual == g.epi.C &&
+                              g.epi.C != nullptr && !g.epi.gelu && g.epi.scale_cols == 0;
+        if (in_place && tiles * 2 <= num_sms) {
+            const int num_k = (g.K + BK - 1) / BK;
+            splits = num_sms / tiles;
+            if (splits > num_k / 4) splits = num_k / 4;       // at least 4 k-slabs per split
+            if (splits > 8) splits = 8;
+            if (splits < 1) splits = 1;
+            const int kbps = (num_k + splits - 1) / splits;
+            splits = (num_k + kbps - 1) / kbps;               // no empty K range
+        }
+        if (splits == 1 && tiles * 2 <= num_sms && g.N >= 64) launch<32, 8>(g, st, num_sms);   // more, narrower tiles
+        else launch<64, 8>(g, st, num_sms, splits);
+    }
 }
 
 }  // namespace wlk

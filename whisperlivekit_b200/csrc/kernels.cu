@@ -209,25 +209,65 @@ void pack_conv_weight(const float* w, void* dst, int dst_type, int c_out, int c_
 // =====================================================================================
 // LayerNorm (fp32 statistics, reference whisper/model.py:39-41), one warp per row
 // =====================================================================================
+// The row (d <= 1280 floats) is read once with 128-bit loads and kept in registers for the two statistics
+// passes and the normalisation; bf16 output is written 8 bytes at a time.
+template <typename TO>
+__device__ __forceinline__ void ln_store4(TO* o, float a, float b, float c, float d);
+template <> __device__ __forceinline__ void ln_store4<float>(float* o, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(o) = make_float4(a, b, c, d);
+}
+template <> __device__ __forceinline__ void ln_store4<bf16>(bf16* o, float a, float b, float c, float d) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(a, b), h1 = __floats2bfloat162_rn(c, d);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(o) = u;
+}
+
 template <typename TO>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ b,
                  TO* __restrict__ out, int64_t ldo, int rows, int d, const int32_t* __restrict__ row_index) {
+    constexpr int MAXV = 10;                          // float4 per lane: d <= 1280
     const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= rows) return;
-    const float* xr = x + (int64_t)(row_index ? row_index[warp] : warp) * ldx;
+    const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)(row_index ? row_index[warp] : warp) * ldx);
+    const int nvec = d >> 2;
+    float4 v[MAXV];
     float s = 0.f;
-    for (int i = lane; i < d; i += 32) s += xr[i];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nvec) { v[i] = xr[idx]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+        else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const float mean = warp_sum(s) / d;
-    float v = 0.f;
-    for (int i = lane; i < d; i += 32) { float t = xr[i] - mean; v = fmaf(t, t, v); }
-    const float rstd = 1.0f / sqrtf(warp_sum(v) / d + 1e-5f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        if (lane + 32 * i < nvec) {
+            float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, dd = v[i].w - mean;
+            q += (a * a + bb * bb) + (c * c + dd * dd);
+        }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / d + 1e-5f);
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
     TO* o = out + (int64_t)warp * ldo;
-    for (int i = lane; i < d; i += 32) o[i] = from_f32<TO>((xr[i] - mean) * rstd * w[i] + b[i]);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < nvec) {
+            const float4 ww = w4[idx], bb = b4[idx];
+            ln_store4<TO>(o + 4 * idx, (v[i].x - mean) * rstd * ww.x + bb.x, (v[i].y - mean) * rstd * ww.y + bb.y,
+                          (v[i].z - mean) * rstd * ww.z + bb.z, (v[i].w - mean) * rstd * ww.w + bb.w);
+        }
+    }
 }
 void layernorm(const float* x, int64_t ldx, const float* w, const float* b, void* out, int out_type, int64_t ldo,
                int rows, int d, const int32_t* row_index, cudaStream_t st) {
     if (rows <= 0) return;
+    WLK_CHECK(d % 4 == 0 && d <= 1280 && ldx % 4 == 0 && ldo % 4 == 0, "layernorm: d=%d must be a multiple of 4 and <= 1280", d);
     int grid = (rows + 7) / 8;
     if (out_type == DT_F32) layernorm_kernel<float><<<grid, 256, 0, st>>>(x, ldx, w, b, (float*)out, ldo, rows, d, row_index);
     else layernorm_kernel<bf16><<<grid, 256, 0, st>>>(x, ldx, w, b, (bf16*)out, ldo, rows, d, row_index);
@@ -377,61 +417,103 @@ void enc_attention_simt(const void* qkv, int type, int batch, int n_head, int d_
     CUDA_CHECK(cudaGetLastError());
 }
 
+template <typename T> struct RowVec;          // 16-byte slice of a 64-wide K/V row held by one lane
+template <> struct RowVec<bf16> {
+    static constexpr int N = 8;
+    typedef uint4 Raw;
+    static __device__ __forceinline__ Raw load(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+    static __device__ __forceinline__ void unpack(const Raw& u, float* o) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { o[2 * i] = __low2float(h[i]); o[2 * i + 1] = __high2float(h[i]); }
+    }
+};
+template <> struct RowVec<float> {
+    static constexpr int N = 4;
+    typedef float4 Raw;
+    static __device__ __forceinline__ Raw load(const float* p) { return *reinterpret_cast<const float4*>(p); }
+    static __device__ __forceinline__ void unpack(const Raw& v, float* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+};
+
+
 // =====================================================================================
 // decoder self-attention over the per-session self-KV cache (causal)
 //   (reference whisper/model.py:109-114,130-146,148-173 with the triu(-inf) mask of :278)
 //   grid (H, jobs), 128 threads; queries processed one after the other
 // =====================================================================================
+// One warp per query row (8 queries in flight per CTA), no block-level synchronisation: lanes own keys
+// lane, lane+32, ... for the scores (whole 64-wide K rows per lane, 128-bit loads), softmax by warp shuffles,
+// then lanes own two output dims each and walk the keys with the probabilities broadcast by shuffle.
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 dec_self_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, int layer, int n_head, int d_model,
                      int n_text_ctx, T* __restrict__ out) {
-    extern __shared__ float sm[];
-    float* sc = sm;                       // [n_text_ctx]
-    float* qs = sc + n_text_ctx;          // [64]
-    float* part = qs + 64;                // [2][64]
-    float* red = part + 128;              // [8]
+    constexpr int MAXK = 14;                 // ceil(448 / 32) keys per lane
+    constexpr int VN = RowVec<T>::N;
+    __shared__ float qs[8][64];
     const DecJob job = jobs[blockIdx.y];
-    const int h = blockIdx.x, tid = threadIdx.x;
+    const int h = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const T* Kc = reinterpret_cast<const T*>(job.self_kv) + (((int64_t)layer * 2 + 0) * n_head + h) * n_text_ctx * 64;
     const T* Vc = reinterpret_cast<const T*>(job.self_kv) + (((int64_t)layer * 2 + 1) * n_head + h) * n_text_ctx * 64;
-    for (int t = 0; t < job.n_rows; ++t) {
+    for (int t = warp; t < job.n_rows; t += 8) {
         const int64_t row = job.row_off + t;
-        const int n_keys = job.offset + t + 1;
-        if (tid < 64) qs[tid] = to_f32(q[row * d_model + h * 64 + tid]);
-        __syncthreads();
-        float lmax = -INFINITY;
-        for (int key = tid; key < n_keys; key += 128) {
-            const T* kr = Kc + (int64_t)key * 64;
-            float s = 0.f;
-#pragma unroll 16
-            for (int e = 0; e < 64; ++e) s = fmaf(qs[e], to_f32(kr[e]), s);
-            sc[key] = s;
-            lmax = fmaxf(lmax, s);
+        const int n_keys = job.offset + t + 1;            // causal: keys 0 .. position
+        qs[warp][lane] = to_f32(q[row * d_model + h * 64 + lane]);
+        qs[warp][lane + 32] = to_f32(q[row * d_model + h * 64 + lane + 32]);
+        __syncwarp();
+        float sc[MAXK];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < MAXK; ++i) {
+            const int key = lane + 32 * i;
+            float a = -INFINITY;
+            if (key < n_keys) {
+                a = 0.f;
+                const T* kr = Kc + (int64_t)key * 64;
+#pragma unroll
+                for (int c = 0; c < 64 / VN; ++c) {
+                    float kv[VN];
+                    RowVec<T>::unpack(RowVec<T>::load(kr + c * VN), kv);
+#pragma unroll
+                    for (int j = 0; j < VN; ++j) a = fmaf(qs[warp][c * VN + j], kv[j], a);
+                }
+            }
+            sc[i] = a;
+            mx = fmaxf(mx, a);
         }
-        const float m = block_max_all<128>(lmax, red);
-        float lsum = 0.f;
-        for (int key = tid; key < n_keys; key += 128) {
-            float p = expf(sc[key] - m);
-            sc[key] = p;
-            lsum += p;
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXK; ++i) {
+            const float p = (lane + 32 * i < n_keys) ? expf(sc[i] - mx) : 0.f;
+            sc[i] = p;
+            sum += p;
         }
-        const float l = block_sum_all<128>(lsum, red);
-        const int g = tid >> 6, e = tid & 63;
-        float acc = 0.f;
-        for (int key = g; key < n_keys; key += 2) acc = fmaf(sc[key], to_f32(Vc[(int64_t)key * 64 + e]), acc);
-        part[g * 64 + e] = acc;
-        __syncthreads();
-        if (tid < 64) out[row * d_model + h * 64 + tid] = from_f32<T>((part[tid] + part[64 + tid]) / l);
-        __syncthreads();
+        sum = warp_sum(sum);
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXK; ++i) {
+            if (32 * i >= n_keys) break;                   // warp-uniform
+            const int lim = min(32, n_keys - 32 * i);
+            for (int l = 0; l < lim; ++l) {
+                const float p = __shfl_sync(0xffffffffu, sc[i], l);
+                const T* vr = Vc + (int64_t)(32 * i + l) * 64 + 2 * lane;
+                o0 = fmaf(p, to_f32(vr[0]), o0);
+                o1 = fmaf(p, to_f32(vr[1]), o1);
+            }
+        }
+        const float inv = 1.0f / sum;
+        out[row * d_model + h * 64 + 2 * lane] = from_f32<T>(o0 * inv);
+        out[row * d_model + h * 64 + 2 * lane + 1] = from_f32<T>(o1 * inv);
+        __syncwarp();
     }
 }
 void dec_self_attention(const void* q, int type, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model,
                         int n_text_ctx, void* out, cudaStream_t st) {
+    WLK_CHECK(n_text_ctx <= 448, "dec_self_attention: n_text_ctx %d > 448", n_text_ctx);
     dim3 grid(n_head, n_jobs);
-    int smem = (n_text_ctx + 64 + 128 + 8) * 4;
-    if (type == DT_F32) dec_self_attn_kernel<float><<<grid, 128, smem, st>>>((const float*)q, jobs, layer, n_head, d_model, n_text_ctx, (float*)out);
-    else dec_self_attn_kernel<bf16><<<grid, 128, smem, st>>>((const bf16*)q, jobs, layer, n_head, d_model, n_text_ctx, (bf16*)out);
+    if (type == DT_F32) dec_self_attn_kernel<float><<<grid, 256, 0, st>>>((const float*)q, jobs, layer, n_head, d_model, n_text_ctx, (float*)out);
+    else dec_self_attn_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)q, jobs, layer, n_head, d_model, n_text_ctx, (bf16*)out);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -442,45 +524,33 @@ void dec_self_attention(const void* q, int type, const DecJob* jobs, int n_jobs,
 //    simul_whisper.py:401-416)
 //   grid (H, jobs), 256 threads, 8 queries per pass
 // =====================================================================================
-template <typename T> struct RowVec;          // 16-byte slice of a 64-wide K/V row held by one lane
-template <> struct RowVec<bf16> {
-    static constexpr int N = 8;
-    static __device__ __forceinline__ void load(const bf16* p, float* o) {
-        uint4 u = *reinterpret_cast<const uint4*>(p);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { o[2 * i] = __low2float(h[i]); o[2 * i + 1] = __high2float(h[i]); }
-    }
-};
-template <> struct RowVec<float> {
-    static constexpr int N = 4;
-    static __device__ __forceinline__ void load(const float* p, float* o) {
-        float4 v = *reinterpret_cast<const float4*>(p);
-        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-    }
-};
-
 // K and V planes are streamed exactly once per block of QB queries with 128-bit loads: a group of LPK lanes
-// covers one 64-wide row, so a warp instruction reads KPW whole rows (512 contiguous bytes).
-template <typename T>
+// covers one 64-wide row, so a warp instruction reads KPW whole rows (512 contiguous bytes); U such loads are
+// issued back to back before any is consumed, which is what keeps enough bytes in flight to cover HBM latency.
+// QB = 1 is the single-token decode step, QB = 8 the prefill.
+template <typename T, int QB>
 __global__ void __launch_bounds__(256)
 dec_cross_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, int layer, int n_head, int d_model,
                       int n_text_ctx, const int32_t* __restrict__ align_rank, T* __restrict__ out) {
-    constexpr int QB = 8;
     constexpr int VN = RowVec<T>::N;          // elements per lane
     constexpr int LPK = 64 / VN;              // lanes per key row  (8 bf16 / 16 fp32)
     constexpr int KPW = 32 / LPK;             // key rows per warp instruction (4 / 2)
+    constexpr int U = 8;                      // loads in flight per lane
+    constexpr int KPI = KPW * U;              // keys per warp per outer iteration
+    constexpr int KEYS_PER_WARP = (N_CTX + 7) / 8;
+    typedef typename RowVec<T>::Raw Raw;
     extern __shared__ float sm[];
     float* sc = sm;                          // [QB][1500]
     float* qs = sc + QB * N_CTX;             // [QB][64]
     float* part = qs + QB * 64;              // [8 warps][QB][64]
     const DecJob job = jobs[blockIdx.y];
     const int h = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int sub = lane / LPK;              // which of the KPW rows of this warp instruction
+    const int sub = lane / LPK;              // which of the KPW rows of a warp instruction
     const int seg = (lane % LPK) * VN;       // first of this lane's VN dims
     const T* Kc = reinterpret_cast<const T*>(job.cross_kv) + (((int64_t)layer * 2 + 0) * n_head + h) * N_CTX * 64;
     const T* Vc = reinterpret_cast<const T*>(job.cross_kv) + (((int64_t)layer * 2 + 1) * n_head + h) * N_CTX * 64;
     const int rank = align_rank[layer * n_head + h];
+    const int kbeg = warp * KEYS_PER_WARP, kend = min(N_CTX, kbeg + KEYS_PER_WARP);
     for (int t0 = 0; t0 < job.n_rows; t0 += QB) {
         const int nq = min(QB, job.n_rows - t0);
         for (int i = tid; i < QB * 64; i += 256) {
@@ -495,27 +565,27 @@ dec_cross_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, 
             for (int qi = 0; qi < QB; ++qi)
 #pragma unroll
                 for (int j = 0; j < VN; ++j) qr[qi][j] = qs[qi * 64 + seg + j];
-            for (int k0 = warp * KPW; k0 < N_CTX; k0 += 8 * KPW) {
-                const int key = k0 + sub;
-                float kv[VN];
-                if (key < N_CTX) RowVec<T>::load(Kc + (int64_t)key * 64 + seg, kv);
-                else {
+            for (int k0 = kbeg; k0 < kend; k0 += KPI) {
+                Raw raw[U];
 #pragma unroll
-                    for (int j = 0; j < VN; ++j) kv[j] = 0.f;
+                for (int u = 0; u < U; ++u) {
+                    const int key = k0 + u * KPW + sub;
+                    raw[u] = RowVec<T>::load(Kc + (int64_t)min(key, N_CTX - 1) * 64 + seg);
                 }
-                float s[QB];
 #pragma unroll
-                for (int qi = 0; qi < QB; ++qi) {
-                    float a = 0.f;
+                for (int u = 0; u < U; ++u) {
+                    const int key = k0 + u * KPW + sub;
+                    float kv[VN];
+                    RowVec<T>::unpack(raw[u], kv);
 #pragma unroll
-                    for (int j = 0; j < VN; ++j) a = fmaf(qr[qi][j], kv[j], a);
+                    for (int qi = 0; qi < QB; ++qi) {
+                        float a = 0.f;
 #pragma unroll
-                    for (int o = LPK / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-                    s[qi] = a;
-                }
-                if ((lane % LPK) == 0 && key < N_CTX) {
+                        for (int j = 0; j < VN; ++j) a = fmaf(qr[qi][j], kv[j], a);
 #pragma unroll
-                    for (int qi = 0; qi < QB; ++qi) sc[qi * N_CTX + key] = s[qi];
+                        for (int o = LPK / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                        if ((lane % LPK) == 0 && key < kend) sc[qi * N_CTX + key] = a;
+                    }
                 }
             }
         }
@@ -546,16 +616,25 @@ dec_cross_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, 
             for (int qi = 0; qi < QB; ++qi)
 #pragma unroll
                 for (int j = 0; j < VN; ++j) acc[qi][j] = 0.f;
-            for (int k0 = warp * KPW; k0 < N_CTX; k0 += 8 * KPW) {
-                const int key = k0 + sub;
-                if (key < N_CTX) {
-                    float vv[VN];
-                    RowVec<T>::load(Vc + (int64_t)key * 64 + seg, vv);
+            for (int k0 = kbeg; k0 < kend; k0 += KPI) {
+                Raw raw[U];
 #pragma unroll
-                    for (int qi = 0; qi < QB; ++qi) {
-                        const float p = sc[qi * N_CTX + key];
+                for (int u = 0; u < U; ++u) {
+                    const int key = k0 + u * KPW + sub;
+                    raw[u] = RowVec<T>::load(Vc + (int64_t)min(key, N_CTX - 1) * 64 + seg);
+                }
 #pragma unroll
-                        for (int j = 0; j < VN; ++j) acc[qi][j] = fmaf(p, vv[j], acc[qi][j]);
+                for (int u = 0; u < U; ++u) {
+                    const int key = k0 + u * KPW + sub;
+                    if (key < kend) {
+                        float vv[VN];
+                        RowVec<T>::unpack(raw[u], vv);
+#pragma unroll
+                        for (int qi = 0; qi < QB; ++qi) {
+                            const float p = sc[qi * N_CTX + key];
+#pragma unroll
+                            for (int j = 0; j < VN; ++j) acc[qi][j] = fmaf(p, vv[j], acc[qi][j]);
+                        }
                     }
                 }
             }
@@ -587,19 +666,30 @@ dec_cross_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, 
         __syncthreads();
     }
 }
-void dec_cross_attention(const void* q, int type, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model,
-                         int n_text_ctx, const int32_t* align_rank, void* out, cudaStream_t st) {
+
+template <typename T, int QB>
+static void launch_cross(const void* q, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model, int n_text_ctx,
+                         const int32_t* align_rank, void* out, cudaStream_t st) {
     dim3 grid(n_head, n_jobs);
-    const int smem = (8 * N_CTX + 8 * 64 + 8 * 8 * 64) * 4;
+    const int smem = (QB * N_CTX + QB * 64 + 8 * QB * 64) * 4;
     static bool set = false;
     if (!set) {
-        CUDA_CHECK(cudaFuncSetAttribute(dec_cross_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CUDA_CHECK(cudaFuncSetAttribute(dec_cross_attn_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_CHECK(cudaFuncSetAttribute(dec_cross_attn_kernel<T, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         set = true;
     }
-    if (type == DT_F32) dec_cross_attn_kernel<float><<<grid, 256, smem, st>>>((const float*)q, jobs, layer, n_head, d_model, n_text_ctx, align_rank, (float*)out);
-    else dec_cross_attn_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)q, jobs, layer, n_head, d_model, n_text_ctx, align_rank, (bf16*)out);
+    dec_cross_attn_kernel<T, QB><<<grid, 256, smem, st>>>((const T*)q, jobs, layer, n_head, d_model, n_text_ctx, align_rank, (T*)out);
     CUDA_CHECK(cudaGetLastError());
+}
+void dec_cross_attention(const void* q, int type, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model,
+                         int n_text_ctx, const int32_t* align_rank, void* out, int max_rows, cudaStream_t st) {
+    const bool single = max_rows <= 1;
+    if (type == DT_F32) {
+        if (single) launch_cross<float, 1>(q, jobs, n_jobs, layer, n_head, d_model, n_text_ctx, align_rank, out, st);
+        else launch_cross<float, 8>(q, jobs, n_jobs, layer, n_head, d_model, n_text_ctx, align_rank, out, st);
+    } else {
+        if (single) launch_cross<bf16, 1>(q, jobs, n_jobs, layer, n_head, d_model, n_text_ctx, align_rank, out, st);
+        else launch_cross<bf16, 8>(q, jobs, n_jobs, layer, n_head, d_model, n_text_ctx, align_rank, out, st);
+    }
 }
 
 // =====================================================================================
