@@ -49,6 +49,11 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r)
           "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
@@ -154,50 +159,65 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, int n_head, int d_mod
             const int n_valid = N_CTX - j * BKV;              // only read when MASKED
             ptx::mbar_wait(bar_s_full, j & 1);
             ptx::tc_fence_after();
+            // Both passes walk S in 16-column chunks with the next chunk's tcgen05.ld already in flight
+            // while the current one is consumed (two register buffers): the TMEM read latency sits behind
+            // the max / exp2 work instead of in front of it.
+            const uint32_t s_addr = tmem + lane_addr + TM_S;
+            uint32_t va[16], vb[16];
             float mx = -INFINITY;
+            ptx::tmem_ld_32x16(s_addr, va);
 #pragma unroll 1
-            for (int c = 0; c < BKV / 32; ++c) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32(tmem + lane_addr + TM_S + c * 32, v);
+            for (int c = 0; c < BKV / 16; c += 2) {
                 ptx::tmem_ld_wait();
+                ptx::tmem_ld_32x16(s_addr + (c + 1) * 16, vb);
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (!MASKED || c * 32 + i < n_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                for (int i = 0; i < 16; ++i)
+                    if (!MASKED || c * 16 + i < n_valid) mx = fmaxf(mx, __uint_as_float(va[i]));
+                ptx::tmem_ld_wait();
+                if (c + 2 < BKV / 16) ptx::tmem_ld_32x16(s_addr + (c + 2) * 16, va);
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (!MASKED || (c + 1) * 16 + i < n_valid) mx = fmaxf(mx, __uint_as_float(vb[i]));
             }
             const float m_new = fmaxf(m, mx * LOG2E);
             const float alpha = fast_exp2(m - m_new);
+            ptx::tmem_ld_32x16(s_addr, va);                    // first chunk of pass 2 flies during the O update
             if (j > 0) {                                      // O_{j-1} joins the accumulator before rescaling
                 ptx::mbar_wait(bar_o_full, (j - 1) & 1);
                 ptx::tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < DH / 32; ++c) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32(tmem + lane_addr + TM_O + c * 32, v);
+                for (int c = 0; c < DH / 16; ++c) {
+                    ptx::tmem_ld_32x16(tmem + lane_addr + TM_O + c * 16, vb);
                     ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[c * 32 + i] = (acc[c * 32 + i] + __uint_as_float(v[i])) * alpha;
+                    for (int i = 0; i < 16; ++i) acc[c * 16 + i] = (acc[c * 16 + i] + __uint_as_float(vb[i])) * alpha;
                 }
             }
             float rs = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < BKV / 32; ++c) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32(tmem + lane_addr + TM_S + c * 32, v);
-                ptx::tmem_ld_wait();
-                uint32_t pk[16];
+            auto emit = [&](const uint32_t* v, int c) {       // 16 scores -> 16 probabilities -> 8 packed words of P
+                uint32_t pk[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < 8; ++i) {
                     float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), LOG2E, -m_new));
                     float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, -m_new));
                     if (MASKED) {
-                        if (c * 32 + 2 * i >= n_valid) p0 = 0.f;
-                        if (c * 32 + 2 * i + 1 >= n_valid) p1 = 0.f;
+                        if (c * 16 + 2 * i >= n_valid) p0 = 0.f;
+                        if (c * 16 + 2 * i + 1 >= n_valid) p1 = 0.f;
                     }
                     rs += p0 + p1;
                     __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
                     pk[i] = *reinterpret_cast<uint32_t*>(&hb);
                 }
-                tmem_st_32x16(tmem + lane_addr + TM_P + c * 16, pk);
+                tmem_st_32x8(tmem + lane_addr + TM_P + c * 8, pk);
+            };
+#pragma unroll 1
+            for (int c = 0; c < BKV / 16; c += 2) {
+                ptx::tmem_ld_wait();
+                ptx::tmem_ld_32x16(s_addr + (c + 1) * 16, vb);
+                emit(va, c);
+                ptx::tmem_ld_wait();
+                if (c + 2 < BKV / 16) ptx::tmem_ld_32x16(s_addr + (c + 2) * 16, va);
+                emit(vb, c + 1);
             }
             ptx::tmem_st_wait();
             l = l * alpha + rs;

@@ -39,7 +39,7 @@ struct DecLayerW {
     void *Wqkv, *Wo, *Wqc, *Woc, *W1, *W2;
 };
 struct Weights {
-    float *filtT, *window; float2* twiddle;
+    float *filtT, *window; float2* twiddle; int2* filt_span;
     void *Wc1, *Wc2; float *bc1, *bc2, *enc_pos;
     std::vector<EncLayerW> enc;
     float *lnpw, *lnpb;
@@ -167,6 +167,7 @@ void layout_weights(wlk_engine* e) {
     W.filtT = f32((size_t)N_FREQ * D.n_mels);
     W.window = f32(N_FFT);
     W.twiddle = reinterpret_cast<float2*>(A.take(N_FFT * 8));
+    W.filt_span = reinterpret_cast<int2*>(A.take((size_t)D.n_mels * 8));
     W.Wc1 = mat((size_t)d * 3 * D.n_mels); W.bc1 = f32(d);
     W.Wc2 = mat((size_t)d * 3 * d); W.bc2 = f32(d);
     W.enc_pos = f32((size_t)D.n_audio_ctx * d);
@@ -242,6 +243,16 @@ void load_tensor(wlk_engine* e, const std::string& name, const float* host, cons
         for (int m = 0; m < D.n_mels; ++m)
             for (int k = 0; k < N_FREQ; ++k) t[(size_t)k * D.n_mels + m] = host[(size_t)m * N_FREQ + k];
         put_f32(e, W.filtT, t.data(), n);
+        std::vector<int2> span(D.n_mels);                     // non-zero span of every (triangular) filter
+        for (int m = 0; m < D.n_mels; ++m) {
+            int lo = N_FREQ, hi = 0;
+            for (int k = 0; k < N_FREQ; ++k)
+                if (host[(size_t)m * N_FREQ + k] != 0.f) { if (k < lo) lo = k; hi = k + 1; }
+            if (lo >= hi) { lo = 0; hi = 0; }
+            span[m] = make_int2(lo, hi);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(W.filt_span, span.data(), span.size() * 8, cudaMemcpyHostToDevice, e->st));
+        CUDA_CHECK(cudaStreamSynchronize(e->st));
     } else if (name == "hann_window") {
         expect(N_FFT);
         put_f32(e, W.window, host, n);
@@ -417,7 +428,7 @@ void encode_batch(wlk_engine* e, const int32_t* sids, int n, int32_t* content_ou
     sg.upload();
 
     {   ProfScope ps(e, WLK_KC_MEL, 0, (double)n * (480000.0 * 4 + 3000.0 * nm * es));
-        mel_forward(mj_dev, n, nm, W.filtT, W.window, W.twiddle, e->act, 0, e->st); }
+        mel_forward(mj_dev, n, nm, W.filtT, W.window, W.twiddle, W.filt_span, e->act, e->st); }
 
     // conv1 (k=3, pad=1) as a GEMM over overlapping rows of the time-major mel: row t = frames t-1..t+1
     {   GemmArgs g;
@@ -1061,7 +1072,7 @@ int wlk_read_mel(wlk_engine* e, int32_t sid, float* out) {
     mj[0].audio = s.audio; mj[0].raw = s.mel_raw; mj[0].blockmax = s.mel_blockmax; mj[0].out = scratch;
     mj[0].n = (int32_t)N; mj[0].n_compute = (int32_t)n_compute; mj[0].n_total = (int32_t)((N + 480000) / HOP); mj[0].pad = 0;
     sg.upload();
-    mel_forward(mj_dev, 1, nm, e->w.filtT, e->w.window, e->w.twiddle, DT_F32, 0, e->st);
+    mel_forward(mj_dev, 1, nm, e->w.filtT, e->w.window, e->w.twiddle, e->w.filt_span, DT_F32, e->st);
     float* h = tap_buffer(e, (size_t)MEL_ROWS * nm);
     CUDA_CHECK(cudaMemcpyAsync(h, scratch, (size_t)MEL_ROWS * nm * 4, cudaMemcpyDeviceToHost, e->st));
     CUDA_CHECK(cudaStreamSynchronize(e->st));

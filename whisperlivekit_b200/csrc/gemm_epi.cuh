@@ -129,6 +129,19 @@ __device__ __forceinline__ void epilogue_warp_tile(const Epilogue& epi, float* s
     __syncwarp();
 }
 
+// Tile rasterisation shared by the three warp roles.  Work item t -> (m block, n block): tiles are walked
+// in bands of `band` m-blocks, n-blocks fastest-but-one inside a band, so the ~num_sms tiles in flight at
+// any time cover one band x a few n-blocks: the band's A rows are fetched from HBM once and then served
+// from L2 for the whole sweep over n, and the few W panels in flight are shared by every CTA.
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int band, int* m_blk, int* n_blk) {
+    const int per_band = band * num_n;
+    const int b = t / per_band;
+    const int r = t - b * per_band;
+    const int h = min(band, num_m - b * band);       // height of this (possibly last, shorter) band
+    *n_blk = r / h;
+    *m_blk = b * band + (r - (*n_blk) * h);
+}
+
 bool make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
                        uint32_t box_rows, uint32_t box_cols, std::string* err);
 

@@ -92,6 +92,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int num_tiles = num_mn * splits;            // split-K: a work item is (k-range, n block, m block)
     const int num_k_total = (K + BK - 1) / BK;
     const int kb_per_split = (num_k_total + splits - 1) / splits;
+    const int band = max(1, (int)gridDim.x / 2);
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
@@ -121,7 +122,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int sp = tile / num_mn, mn = tile - sp * num_mn;
-                const int m_blk = mn % num_m, n_blk = mn / num_m;
+                int m_blk, n_blk;
+                tile_coords(mn, num_m, num_n, band, &m_blk, &n_blk);
                 const int kb_end = min(num_k_total, (sp + 1) * kb_per_split);
                 for (int kb = sp * kb_per_split; kb < kb_end; ++kb) {
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -171,7 +173,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int sp = tile / num_mn, mn = tile - sp * num_mn;
-            const int m_blk = mn % num_m, n_blk = mn / num_m;
+            int m_blk, n_blk;
+            tile_coords(mn, num_m, num_n, band, &m_blk, &n_blk);
             const uint32_t as = it & 1, ap = (it >> 1) & 1;
             const EpiRow row = epi_row(epi, m_blk * BM + q * 32 + lane, M);
             ptx::mbar_wait(bar_tfull + 8 * as, ap);

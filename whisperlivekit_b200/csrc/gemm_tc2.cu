@@ -105,6 +105,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int num_m = (M + BM2 - 1) / BM2, num_n = (N + BN2 - 1) / BN2;
     const int num_tiles = num_m * num_n;
     const int num_k = (K + BK2 - 1) / BK2;
+    const int band = max(1, num_clusters / 2);        // two n-blocks of a band in flight at a time
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
@@ -134,7 +135,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                const int m_blk = tile % num_m, n_blk = tile / num_m;
+                int m_blk, n_blk;
+                tile_coords(tile, num_m, num_n, band, &m_blk, &n_blk);
                 for (int kb = 0; kb < num_k; ++kb) {
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     if (leader) ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * (A_BYTES2 + B_BYTES2));
@@ -179,7 +181,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         float* sbias = reinterpret_cast<float*>(smem_gen + STG_OFF2) + ew * EPI_BIAS_FLOATS;
         uint32_t it = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
-            const int m_blk = tile % num_m, n_blk = tile / num_m;
+            int m_blk, n_blk;
+            tile_coords(tile, num_m, num_n, band, &m_blk, &n_blk);
             const uint32_t as = it & 1, ap = (it >> 1) & 1;
             const EpiRow row = epi_row(epi, m_blk * BM2 + rank * 128 + q * 32 + lane, M);
             ptx::mbar_wait(bar_tfull + 8 * as, ap);

@@ -12,7 +12,7 @@ constexpr int N_CTX = 1500;
 constexpr int N_FREQ = 201;
 constexpr int N_FFT = 400;
 constexpr int HOP = 160;
-constexpr int MEL_FRAMES_PER_CTA = 8;
+constexpr int MEL_FRAMES_PER_CTA = 16;
 constexpr int MEL_MAX_CTAS = (N_FRAMES + 2 + MEL_FRAMES_PER_CTA - 1) / MEL_FRAMES_PER_CTA;   // 376
 
 struct MelJob {                 // one per session in the batch (device array)
@@ -26,8 +26,8 @@ struct MelJob {                 // one per session in the batch (device array)
     int32_t pad;
 };
 
-void mel_forward(const MelJob* jobs_dev, int batch, int n_mels, const float* filters, const float* window,
-                 const float2* twiddle, int out_type, int max_compute_frames, cudaStream_t st);
+void mel_forward(const MelJob* jobs_dev, int batch, int n_mels, const float* filtT, const float* window,
+                 const float2* twiddle, const int2* filt_span, int out_type, cudaStream_t st);
 
 void zero_rows(void* base, int type, int64_t row_elems, const int64_t* row_index_dev, int n_rows, cudaStream_t st);
 
