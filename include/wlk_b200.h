@@ -124,6 +124,14 @@ int wlk_op_mel(wlk_engine* e, const float* audio_dev, int64_t n_samples, float* 
                int32_t* content_mel_len);
 int wlk_op_encoder_attention(wlk_engine* e, int backend, const void* qkv, int type, int batch, void* out);
 
+/* ---- word-timestamp kernels of the LocalAgreement path: native replacements of the reference's Triton
+ *      median_kernel / dtw_kernel (whisper/triton_ops.py:13-103) with the semantics of its CPU path
+ *      (whisper/timing.py:19-54 median_filter; :57-105 dtw_cpu + backtrace).  x is device fp32.
+ *      wlk_op_dtw: x[N tokens, M frames] -> alignment path (text_idx[i], time_idx[i]), i < *len <= N+M.   */
+int wlk_op_median_filter(wlk_engine* e, const float* x_dev, float* out_dev, int rows, int cols, int width);
+int wlk_op_dtw(wlk_engine* e, const float* x_dev, int N, int M, int32_t* text_idx_host, int32_t* time_idx_host,
+               int32_t* len_out);
+
 /* ---- device timers + per-kernel-class profile (CUDA events on the engine stream) ------- */
 int wlk_timer_record(wlk_engine* e, int slot);                 /* slot in [0,16) */
 int wlk_timer_elapsed_ms(wlk_engine* e, int from_slot, int to_slot, float* ms);

@@ -204,6 +204,30 @@ def filters_fixture():
     return out
 
 
+def timing_fixture():
+    """Reference median_filter (torch CPU path) and dtw_cpu (numba) on seeded attention-like matrices."""
+    from whisperlivekit.whisper.timing import dtw_cpu, median_filter
+    rng = np.random.default_rng(7)
+    out = {}
+    for idx, (n, m) in enumerate([(5, 40), (23, 310), (61, 750), (1, 12), (9, 9)]):
+        a = rng.random((n, m)).astype(np.float32)
+        a = a / a.sum(-1, keepdims=True)
+        a[np.arange(n), np.minimum(m - 1, (np.arange(n) * m) // max(n, 1))] += 0.5      # a noisy diagonal ridge
+        z = (a - a.mean(0, keepdims=True)) / (a.std(0, keepdims=True) + 1e-8)
+        med = median_filter(torch.from_numpy(z), 7).numpy()
+        ti, fi = dtw_cpu((-med).astype(np.float64))
+        out[f"x{idx}"] = z.astype(np.float32)
+        out[f"med{idx}"] = med.astype(np.float32)
+        out[f"text{idx}"] = np.asarray(ti, np.int64)
+        out[f"time{idx}"] = np.asarray(fi, np.int64)
+    # ties: quantised costs make equal-cost moves frequent, pinning the move preference
+    q = np.round(rng.random((17, 90)) * 4).astype(np.float32) / 4
+    ti, fi = dtw_cpu(q.astype(np.float64))
+    out["xq"], out["textq"], out["timeq"] = q, np.asarray(ti, np.int64), np.asarray(fi, np.int64)
+    out["n_cases"] = np.int64(5)
+    return out
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -211,6 +235,7 @@ def main():
     gdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gdir, exist_ok=True)
     np.savez_compressed(os.path.join(gdir, "mel_filters.npz"), **filters_fixture())
+    np.savez_compressed(os.path.join(gdir, "timing.npz"), **timing_fixture())
     only = sys.argv[1:]
     for name, spec in CASES.items():
         if only and name not in only:

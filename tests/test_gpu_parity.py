@@ -159,3 +159,34 @@ def test_large_v3_fp32_logits_match_oracle():
     r_e, r_o = eng.greedy_and_align([se])[0], orc.greedy_and_align([so])[0]
     assert r_e[0] == r_o[0] and r_e[2] == r_o[2] and abs(r_e[1] - r_o[1]) < 1e-3
     eng.close()
+
+
+def test_bf16_prefill_cross_attention_on_tensor_cores():
+    """A 40-token prefill takes the tcgen05 cross-attention path (non-alignment heads) in bf16 mode;
+    it must agree with the SIMT path of the same precision mode and with the CPU oracle."""
+    from oracle import whisper_oracle as wo
+    from whisperlivekit_b200.engine import WhisperEngine
+    for k in list(_ENGINES):
+        _ENGINES.pop(k).close()
+    g, dims, sd, audio, heads = case_setup("tiny")
+    prefix = list(g["forced_prefix"]) + [int(t) for t in range(1000, 1033)]
+    outs = {}
+    for backend in ("tcgen05", "simt"):
+        eng = WhisperEngine(dims, sd, heads, precision="bf16", max_sessions=2, max_batch=2, attn_backend=backend)
+        s0, s1 = eng.open_session(), eng.open_session()
+        eng.append_audio(s0, audio); eng.append_audio(s1, audio[:40000])
+        eng.encode([s0, s1])
+        eng.decode([s0, s1], [prefix, prefix[:25]])
+        eng.decode([s0, s1], [[1169], [2068]])
+        outs[backend] = (eng.read_logits(s0), eng.read_logits(s1), eng.greedy_and_align([s0, s1]))
+        eng.close()
+    orc = wo.OracleEngine(dims, sd, heads)
+    so = orc.open_session()
+    orc.append_audio(so, audio); orc.encode([so]); orc.decode([so], [prefix]); orc.decode([so], [[1169]])
+    ref = orc.read_logits(so)
+    for i in (0, 1):
+        assert np.abs(outs["tcgen05"][i] - outs["simt"][i]).max() < 6e-2
+    assert np.abs(outs["tcgen05"][0] - ref).max() < 1e-1
+    assert np.abs(outs["simt"][0] - ref).max() < 1e-1
+    # the alignment rows come from the same (SIMT, exact-softmax) kernel in both configurations
+    assert outs["tcgen05"][2][0][2] == outs["simt"][2][0][2]

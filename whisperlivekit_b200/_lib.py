@@ -69,6 +69,8 @@ SIGNATURES = {
                               _vp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int]),
     "wlk_op_mel": (C.c_int, [_vp, _vp, C.c_int64, _vp, _i32p]),
     "wlk_op_encoder_attention": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp]),
+    "wlk_op_median_filter": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int]),
+    "wlk_op_dtw": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _i32p]),
     "wlk_timer_record": (C.c_int, [_vp, C.c_int]),
     "wlk_timer_elapsed_ms": (C.c_int, [_vp, C.c_int, C.c_int, _f32p]),
     "wlk_profile_enable": (C.c_int, [_vp, C.c_int]),

@@ -65,8 +65,17 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
         : "memory");
 }
 
+// CROSS = false: encoder self-attention, Q/K/V tiles all come out of the fused qkv buffer (tensor map `tm`).
+// CROSS = true : decoder cross-attention of a prefill (many query rows per session): Q tiles from the packed
+//                query buffer (`tm`), K/V tiles from the session's head-major cross-K/V planes through a
+//                per-session tensor map kept in global memory (`kv_maps[job.slot]`).  Alignment heads are
+//                skipped here: their rows need the exactly normalised probabilities exported, which the
+//                SIMT kernel produces.
+template <bool CROSS>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
-enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, int n_head, int d_model, bf16* __restrict__ out) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const CUtensorMap* __restrict__ kv_maps,
+               const DecJob* __restrict__ jobs, int layer, const int32_t* __restrict__ align_rank,
+               int n_head, int d_model, bf16* __restrict__ out) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - ptx::smem_u32(smem_raw));
@@ -82,11 +91,30 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, int n_head, int d_mod
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
-    const int row0 = b * N_CTX;                          // first row of this stream in the qkv buffer
     constexpr int NT = (N_CTX + BKV - 1) / BKV;          // 12 key tiles
+    // tile origins (tensor-map coordinates) and the number of query rows this CTA owns
+    const CUtensorMap* tm_kv = &tm;
+    int q_row, q_col = h * DH, k_row, k_col, v_row, v_col, out_row, n_q;
+    if constexpr (CROSS) {
+        const DecJob job = jobs[b];
+        if (q0 >= job.n_rows || align_rank[layer * n_head + h] >= 0) return;     // uniform: before any barrier / TMEM use
+        tm_kv = kv_maps + job.slot;
+        q_row = job.row_off + q0;
+        k_row = (((layer * 2 + 0) * n_head) + h) * N_CTX; k_col = 0;
+        v_row = (((layer * 2 + 1) * n_head) + h) * N_CTX; v_col = 0;
+        out_row = job.row_off + q0;
+        n_q = min(BQ, job.n_rows - q0);
+    } else {
+        q_row = b * N_CTX + q0;
+        k_row = b * N_CTX; k_col = d_model + h * DH;
+        v_row = b * N_CTX; v_col = 2 * d_model + h * DH;
+        out_row = b * N_CTX + q0;
+        n_q = min(BQ, N_CTX - q0);
+    }
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tm);
+        if (CROSS) ptx::prefetch_tensormap(tm_kv);
         ptx::mbar_init(bar_q, 1);
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_kv_full + 8 * i, 1); ptx::mbar_init(bar_kv_empty + 8 * i, 1); }
         ptx::mbar_init(bar_s_full, 1);
@@ -104,13 +132,13 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, int n_head, int d_mod
     if (warp == 0) {
         if (lane == 0) {
             ptx::mbar_arrive_expect_tx(bar_q, TILE_BYTES);
-            ptx::tma_load_2d(sbase + SM_Q, &tm, bar_q, h * DH, row0 + q0);
+            ptx::tma_load_2d(sbase + SM_Q, &tm, bar_q, q_col, q_row);
             for (int j = 0; j < NT; ++j) {
                 const uint32_t s = j & 1, ph = (j >> 1) & 1;
                 ptx::mbar_wait(bar_kv_empty + 8 * s, ph ^ 1);
                 ptx::mbar_arrive_expect_tx(bar_kv_full + 8 * s, 2 * TILE_BYTES);
-                ptx::tma_load_2d(sbase + SM_K + s * TILE_BYTES, &tm, bar_kv_full + 8 * s, d_model + h * DH, row0 + j * BKV);
-                ptx::tma_load_2d(sbase + SM_V + s * TILE_BYTES, &tm, bar_kv_full + 8 * s, 2 * d_model + h * DH, row0 + j * BKV);
+                ptx::tma_load_2d(sbase + SM_K + s * TILE_BYTES, tm_kv, bar_kv_full + 8 * s, k_col, k_row + j * BKV);
+                ptx::tma_load_2d(sbase + SM_V + s * TILE_BYTES, tm_kv, bar_kv_full + 8 * s, v_col, v_row + j * BKV);
             }
         }
     } else if (warp == 1) {
@@ -239,9 +267,9 @@ enc_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, int n_head, int d_mod
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[c * 32 + i] += __uint_as_float(v[i]);
         }
-        if (q0 + r < N_CTX) {
+        if (r < n_q) {
             const float inv = 1.0f / l;
-            bf16* o = out + (int64_t)(row0 + q0 + r) * d_model + h * DH;
+            bf16* o = out + (int64_t)(out_row + r) * d_model + h * DH;
 #pragma unroll
             for (int e8 = 0; e8 < DH / 8; ++e8) {
                 uint4 u;
@@ -270,11 +298,38 @@ void enc_attention_tcgen05(const void* qkv, int batch, int n_head, int d_model, 
               "qkv tensor map: %s", err.c_str());
     static bool set = false;
     if (!set) {
-        CUDA_CHECK(cudaFuncSetAttribute(enc_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
         set = true;
     }
     dim3 grid((N_CTX + BQ - 1) / BQ, n_head, batch);
-    enc_attn_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm, n_head, d_model, reinterpret_cast<bf16*>(out));
+    attn_tc_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm, nullptr, nullptr, 0, nullptr, n_head, d_model,
+                                                              reinterpret_cast<bf16*>(out));
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// tensor map over one session's cross-K/V planes viewed as [L * 2 * H * 1500 rows, 64] bf16
+void make_cross_kv_tmap(void* tmap_out_host, const void* cross_kv, int n_layer, int n_head) {
+    std::string err;
+    WLK_CHECK(make_tmap_bf16_2d(reinterpret_cast<CUtensorMap*>(tmap_out_host), cross_kv,
+                                (uint64_t)n_layer * 2 * n_head * N_CTX, DH, DH, BKV, DH, &err),
+              "cross-K/V tensor map: %s", err.c_str());
+}
+
+void dec_cross_attention_tcgen05(const void* q, int total_rows, const DecJob* jobs, int n_jobs, int max_rows, int layer,
+                                 int n_head, int d_model, const void* kv_maps_dev, const int32_t* align_rank, void* out,
+                                 cudaStream_t st) {
+    CUtensorMap tm;
+    std::string err;
+    WLK_CHECK(make_tmap_bf16_2d(&tm, q, (uint64_t)total_rows, (uint64_t)d_model, (uint64_t)d_model, BQ, DH, &err),
+              "query tensor map: %s", err.c_str());
+    static bool set = false;
+    if (!set) {
+        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+        set = true;
+    }
+    dim3 grid((max_rows + BQ - 1) / BQ, n_head, n_jobs);
+    attn_tc_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm, reinterpret_cast<const CUtensorMap*>(kv_maps_dev), jobs, layer,
+                                                             align_rank, n_head, d_model, reinterpret_cast<bf16*>(out));
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -87,6 +87,7 @@ struct wlk_engine {
     std::vector<Session> sess;
     std::vector<int32_t> align_rank_host;     // [L*H] -> rank or -1
     int32_t* align_rank_dev = nullptr;
+    uint8_t* kv_maps_dev = nullptr;           // [max_sessions] CUtensorMap (128 B each) over each session's cross-K/V
     int n_align = 0;
 
     // encoder workspace (max_batch streams)
@@ -545,6 +546,7 @@ void decode_batch(wlk_engine* e, const int32_t* sids, int n, const int32_t* toke
         dj[i].self_kv = s.self_kv; dj[i].cross_kv = s.cross_kv; dj[i].align = s.align;
         dj[i].logits_last = s.logits_last; dj[i].logits_sot = s.logits_sot;
         dj[i].row_off = r; dj[i].n_rows = tq; dj[i].offset = s.self_len; dj[i].align_row0 = s.align_rows;
+        dj[i].slot = sids[i]; dj[i].pad0 = dj[i].pad1 = dj[i].pad2 = 0;
         skv[i] = s.self_kv;
         for (int t = 0; t < tq; ++t, ++r) {
             int32_t tk = tokens[offsets[i] - offsets[0] + t];
@@ -587,7 +589,11 @@ void decode_batch(wlk_engine* e, const int32_t* sids, int n, const int32_t* toke
             g.epi.C = e->dq; g.epi.c_type = e->act; g.epi.ldc = dt;
             run_gemm(e, g, WLK_KC_GEMM_DEC); }
         {   ProfScope ps(e, WLK_KC_ATTN_DEC_CROSS, 0, (double)n * 2 * H * N_CTX * 64 * es);
-            dec_cross_attention(e->dq, e->act, dj_dev, n, li, H, dt, ctx, e->align_rank_dev, e->datt, max_tq, e->st); }
+            const bool tc_prefill = e->attn_backend == WLK_BACKEND_TCGEN05 && e->act == DT_BF16 && max_tq >= 16;
+            if (tc_prefill)     // all non-alignment heads on the tensor cores; alignment heads need the exported rows
+                dec_cross_attention_tcgen05(e->dq, R, dj_dev, n, max_tq, li, H, dt, e->kv_maps_dev, e->align_rank_dev,
+                                            e->datt, e->st);
+            dec_cross_attention(e->dq, e->act, dj_dev, n, li, H, dt, ctx, e->align_rank_dev, e->datt, max_tq, tc_prefill, e->st); }
         {   GemmArgs g;
             g.A = e->datt; g.a_type = e->act; g.lda = dt; g.W = L.Woc; g.w_type = e->act; g.ldw = dt;
             g.M = R; g.N = dt; g.K = dt;
@@ -654,6 +660,12 @@ void alloc_session(wlk_engine* e, Session& s) {
     s.attn_out = dmalloc<float>(e, (size_t)D.n_text_ctx * N_CTX, acct);
     s.stats = dmalloc<float>(e, (size_t)(e->n_align > 0 ? e->n_align : 1) * N_CTX * 2, acct);
     e->bytes_sessions += s.bytes;
+    if (e->act == DT_BF16) {
+        alignas(64) uint8_t tmap[128];
+        make_cross_kv_tmap(tmap, s.cross_kv, D.n_text_layer, D.n_text_head);
+        const size_t slot = (size_t)(&s - e->sess.data());
+        CUDA_CHECK(cudaMemcpy(e->kv_maps_dev + slot * 128, tmap, 128, cudaMemcpyHostToDevice));
+    }
 }
 void free_session(wlk_engine* e, Session& s) {
     void* ptrs[] = {s.audio, s.mel_raw, s.mel_blockmax, s.xa, s.cross_kv, s.self_kv, s.align, s.logits_last,
@@ -752,6 +764,7 @@ void create_engine(const wlk_dims* dims, const wlk_config* cfg, wlk_engine** out
     e->res_dev = dmalloc<StepResult>(e, B, acct);
     CUDA_CHECK(cudaMallocHost(&e->res_host, sizeof(StepResult) * B));
     e->sess.resize(cfg->max_sessions);
+    e->kv_maps_dev = reinterpret_cast<uint8_t*>(dmalloc_bytes((size_t)cfg->max_sessions * 128, acct));
     e->align_rank_host.assign((size_t)D.n_text_layer * D.n_text_head, -1);
     e->align_rank_dev = dmalloc<int32_t>(e, e->align_rank_host.size(), acct);
     CUDA_CHECK(cudaMemcpy(e->align_rank_dev, e->align_rank_host.data(), e->align_rank_host.size() * 4, cudaMemcpyHostToDevice));
@@ -763,7 +776,7 @@ void destroy_engine(wlk_engine* e) {
     for (auto& s : e->sess) if (s.open) free_session(e, s);
     void* ptrs[] = {e->arena.base, e->stage_f32, e->mel_t, e->h1, e->x, e->xn, e->qkv, e->att, e->hid, e->audio_scratch, e->mel_scratch,
                     e->pad_rows_dev, e->xptrs_dev, e->dx, e->dxn, e->dq, e->datt, e->dhid, e->dsel, e->stg_dev,
-                    e->res_dev, e->align_rank_dev};
+                    e->res_dev, e->align_rank_dev, e->kv_maps_dev};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->stg_host) cudaFreeHost(e->stg_host);
     if (e->res_host) cudaFreeHost(e->res_host);
@@ -1152,6 +1165,42 @@ int wlk_op_encoder_attention(wlk_engine* e, int backend, const void* qkv, int ty
     } else {
         enc_attention_simt(qkv, type, batch, e->dims.n_audio_head, e->dims.n_audio_state, out, e->st);
     }
+    WLK_API_END
+}
+
+int wlk_op_median_filter(wlk_engine* e, const float* x_dev, float* out_dev, int rows, int cols, int width) {
+    WLK_API_BEGIN
+    LOCK(e);
+    WLK_CHECK(x_dev && out_dev && rows >= 1 && cols >= 1, "bad arguments");
+    ProfScope ps(e, WLK_KC_ALIGN);
+    median_filter(x_dev, out_dev, rows, cols, width, e->st);
+    WLK_API_END
+}
+int wlk_op_dtw(wlk_engine* e, const float* x_dev, int N, int M, int32_t* text_idx_host, int32_t* time_idx_host,
+               int32_t* len_out) {
+    WLK_API_BEGIN
+    LOCK(e);
+    WLK_CHECK(x_dev && text_idx_host && time_idx_host && len_out, "null argument");
+    WLK_CHECK(N >= 1 && N <= 4096 && M >= 1 && M <= 8192, "dtw: shape %d x %d out of range", N, M);
+    size_t acct = 0;
+    uint8_t* trace = dmalloc<uint8_t>(e, (size_t)(N + 1) * (M + 1), &acct);
+    int32_t* path = dmalloc<int32_t>(e, (size_t)4 * (N + M) + 4, &acct);
+    int32_t* plen = dmalloc<int32_t>(e, 1, &acct);
+    DtwJobHost* job_dev = dmalloc<DtwJobHost>(e, 1, &acct);
+    DtwJobHost job{x_dev, trace, path, plen, N, M};
+    CUDA_CHECK(cudaMemcpyAsync(job_dev, &job, sizeof(job), cudaMemcpyHostToDevice, e->st));
+    {   ProfScope ps(e, WLK_KC_ALIGN);
+        dtw_batch(job_dev, 1, N, e->st); }
+    std::vector<int32_t> host((size_t)2 * (N + M));
+    int32_t n = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&n, plen, 4, cudaMemcpyDeviceToHost, e->st));
+    CUDA_CHECK(cudaMemcpyAsync(host.data(), path, host.size() * 4, cudaMemcpyDeviceToHost, e->st));
+    CUDA_CHECK(cudaStreamSynchronize(e->st));
+    cudaFree(trace); cudaFree(path); cudaFree(plen); cudaFree(job_dev);
+    WLK_CHECK(n >= 1 && n <= N + M, "dtw: bad path length %d", n);
+    memcpy(text_idx_host, host.data(), (size_t)n * 4);
+    memcpy(time_idx_host, host.data() + (N + M), (size_t)n * 4);
+    *len_out = n;
     WLK_API_END
 }
 

@@ -561,7 +561,7 @@ void dec_self_attention(const void* q, int type, const DecJob* jobs, int n_jobs,
 template <typename T, int QB>
 __global__ void __launch_bounds__(256)
 dec_cross_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, int layer, int n_head, int d_model,
-                      int n_text_ctx, const int32_t* __restrict__ align_rank, T* __restrict__ out) {
+                      int n_text_ctx, const int32_t* __restrict__ align_rank, T* __restrict__ out, int only_align) {
     constexpr int VN = RowVec<T>::N;          // elements per lane
     constexpr int LPK = 64 / VN;              // lanes per key row  (8 bf16 / 16 fp32)
     constexpr int KPW = 32 / LPK;             // key rows per warp instruction (4 / 2)
@@ -580,6 +580,7 @@ dec_cross_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, 
     const T* Kc = reinterpret_cast<const T*>(job.cross_kv) + (((int64_t)layer * 2 + 0) * n_head + h) * N_CTX * 64;
     const T* Vc = reinterpret_cast<const T*>(job.cross_kv) + (((int64_t)layer * 2 + 1) * n_head + h) * N_CTX * 64;
     const int rank = align_rank[layer * n_head + h];
+    if (only_align && rank < 0) return;      // the other heads were done on the tensor cores
     const int kbeg = warp * KEYS_PER_WARP, kend = min(N_CTX, kbeg + KEYS_PER_WARP);
     for (int t0 = 0; t0 < job.n_rows; t0 += QB) {
         const int nq = min(QB, job.n_rows - t0);
@@ -699,7 +700,7 @@ dec_cross_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, 
 
 template <typename T, int QB>
 static void launch_cross(const void* q, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model, int n_text_ctx,
-                         const int32_t* align_rank, void* out, cudaStream_t st) {
+                         const int32_t* align_rank, void* out, int only_align, cudaStream_t st) {
     dim3 grid(n_head, n_jobs);
     const int smem = (QB * N_CTX + QB * 64 + 8 * QB * 64) * 4;
     static bool set = false;
@@ -707,18 +708,20 @@ static void launch_cross(const void* q, const DecJob* jobs, int n_jobs, int laye
         CUDA_CHECK(cudaFuncSetAttribute(dec_cross_attn_kernel<T, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         set = true;
     }
-    dec_cross_attn_kernel<T, QB><<<grid, 256, smem, st>>>((const T*)q, jobs, layer, n_head, d_model, n_text_ctx, align_rank, (T*)out);
+    dec_cross_attn_kernel<T, QB><<<grid, 256, smem, st>>>((const T*)q, jobs, layer, n_head, d_model, n_text_ctx, align_rank, (T*)out, only_align);
     CUDA_CHECK(cudaGetLastError());
 }
 void dec_cross_attention(const void* q, int type, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model,
-                         int n_text_ctx, const int32_t* align_rank, void* out, int max_rows, cudaStream_t st) {
+                         int n_text_ctx, const int32_t* align_rank, void* out, int max_rows, bool only_align_heads,
+                         cudaStream_t st) {
     const bool single = max_rows <= 1;
+    const int oa = only_align_heads ? 1 : 0;
     if (type == DT_F32) {
-        if (single) launch_cross<float, 1>(q, jobs, n_jobs, layer, n_head, d_model, n_text_ctx, align_rank, out, st);
-        else launch_cross<float, 8>(q, jobs, n_jobs, layer, n_head, d_model, n_text_ctx, align_rank, out, st);
+        if (single) launch_cross<float, 1>(q, jobs, n_jobs, layer, n_head, d_model, n_text_ctx, align_rank, out, oa, st);
+        else launch_cross<float, 8>(q, jobs, n_jobs, layer, n_head, d_model, n_text_ctx, align_rank, out, oa, st);
     } else {
-        if (single) launch_cross<bf16, 1>(q, jobs, n_jobs, layer, n_head, d_model, n_text_ctx, align_rank, out, st);
-        else launch_cross<bf16, 8>(q, jobs, n_jobs, layer, n_head, d_model, n_text_ctx, align_rank, out, st);
+        if (single) launch_cross<bf16, 1>(q, jobs, n_jobs, layer, n_head, d_model, n_text_ctx, align_rank, out, oa, st);
+        else launch_cross<bf16, 8>(q, jobs, n_jobs, layer, n_head, d_model, n_text_ctx, align_rank, out, oa, st);
     }
 }
 
@@ -897,6 +900,102 @@ void align_reduce(const LogitJob* jobs, int n, int n_align, int n_text_ctx, Step
     align_rows_kernel<<<g2, 256, 0, st>>>(jobs, n_align, n_text_ctx);
     CUDA_CHECK(cudaGetLastError());
     align_argmax_kernel<<<n, 256, 0, st>>>(jobs, res);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+
+// =====================================================================================
+// Word-timestamp kernels of the LocalAgreement path: native replacements of the reference's two Triton
+// kernels (whisper/triton_ops.py:13-103) with the semantics of its CPU path, which is the parity oracle
+// (whisper/timing.py:19-54 median_filter, :57-105 dtw_cpu + backtrace).
+// =====================================================================================
+// median over a sliding window of odd width <= 15 along the last axis, reflect padding (no edge repeat)
+__global__ void __launch_bounds__(256)
+median_filter_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int cols, int width) {
+    const int r = blockIdx.y;
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (r >= rows || c >= cols) return;
+    const float* xr = x + (int64_t)r * cols;
+    const int pad = width / 2;
+    float v[15];
+    for (int j = 0; j < width; ++j) {
+        int g = c + j - pad;
+        if (g < 0) g = -g;
+        if (g >= cols) g = 2 * (cols - 1) - g;
+        v[j] = xr[g];
+    }
+    for (int a = 1; a < width; ++a) {                 // insertion sort (width is tiny)
+        float key = v[a];
+        int b = a - 1;
+        while (b >= 0 && v[b] > key) { v[b + 1] = v[b]; --b; }
+        v[b + 1] = key;
+    }
+    out[(int64_t)r * cols + c] = v[pad];
+}
+void median_filter(const float* x, float* out, int rows, int cols, int width, cudaStream_t st) {
+    WLK_CHECK(width >= 1 && width <= 15 && (width & 1), "median_filter: width %d must be odd and <= 15", width);
+    if (cols <= width / 2) {                          // timing.py:22-24: too short to pad, returned unchanged
+        CUDA_CHECK(cudaMemcpyAsync(out, x, (size_t)rows * cols * 4, cudaMemcpyDeviceToDevice, st));
+        return;
+    }
+    dim3 grid((cols + 255) / 256, rows);
+    median_filter_kernel<<<grid, 256, 0, st>>>(x, out, rows, cols, width);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// Dynamic time warping over x[N tokens, M frames]: anti-diagonal wavefront (thread = token row), three
+// rotating diagonals in shared memory, byte trace in global memory, then the serial backtrace by one thread.
+// Move choice follows dtw_cpu exactly: diagonal only if strictly cheaper than both, else up only if
+// strictly cheaper than both, else left.  One CTA per problem (blockIdx.x = problem index).
+struct DtwJob { const float* x; uint8_t* trace; int32_t* path; int32_t* path_len; int32_t N, M; };
+
+__global__ void __launch_bounds__(512)
+dtw_kernel(const DtwJob* __restrict__ jobs) {
+    extern __shared__ float dsm[];
+    const DtwJob job = jobs[blockIdx.x];
+    const int N = job.N, M = job.M, tid = threadIdx.x;
+    float* d0 = dsm;                       // diagonal k-2
+    float* d1 = dsm + (N + 1);             // diagonal k-1
+    float* d2 = dsm + 2 * (N + 1);         // diagonal k
+    for (int i = tid; i <= N; i += 512) { d0[i] = INFINITY; d1[i] = INFINITY; d2[i] = INFINITY; }
+    __syncthreads();
+    if (tid == 0) d0[0] = 0.f;             // cost[0][0]; diagonal 1 (cost[0][1], cost[1][0]) stays inf
+    __syncthreads();
+    for (int k = 2; k <= N + M; ++k) {
+        const int lo = max(1, k - M), hi = min(N, k - 1);
+        for (int i = lo + tid; i <= hi; i += 512) {
+            const int j = k - i;
+            const float c0 = d0[i - 1], c1 = d1[i - 1], c2 = d1[i];
+            float c; uint8_t t;
+            if (c0 < c1 && c0 < c2) { c = c0; t = 0; }
+            else if (c1 < c0 && c1 < c2) { c = c1; t = 1; }
+            else { c = c2; t = 2; }
+            d2[i] = __fadd_rn(job.x[(int64_t)(i - 1) * M + (j - 1)], c);
+            job.trace[(int64_t)i * (M + 1) + j] = t;
+        }
+        if (tid == 0) { d2[0] = INFINITY; if (k <= N) d2[k] = INFINITY; }   // cost[0][k], cost[k][0]
+        __syncthreads();
+        float* tmp = d0; d0 = d1; d1 = d2; d2 = tmp;
+        __syncthreads();
+    }
+    if (tid == 0) {                        // backtrace (timing.py:57-79), written in forward order
+        int i = N, j = M, n = 0;
+        int32_t* tmp = job.path + 2 * (N + M);           // scratch behind the two output rows
+        while (i > 0 || j > 0) {
+            tmp[2 * n] = i - 1; tmp[2 * n + 1] = j - 1; ++n;
+            const int t = (i == 0) ? 2 : (j == 0) ? 1 : job.trace[(int64_t)i * (M + 1) + j];
+            if (t == 0) { --i; --j; } else if (t == 1) --i; else --j;
+        }
+        for (int q = 0; q < n; ++q) {
+            job.path[q] = tmp[2 * (n - 1 - q)];                 // text (token) indices
+            job.path[(N + M) + q] = tmp[2 * (n - 1 - q) + 1];   // time (frame) indices
+        }
+        *job.path_len = n;
+    }
+}
+void dtw_batch(const void* jobs_dev, int n_jobs, int max_tokens, cudaStream_t st) {
+    const int smem = 3 * (max_tokens + 1) * 4;
+    dtw_kernel<<<n_jobs, 512, smem, st>>>(reinterpret_cast<const DtwJob*>(jobs_dev));
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -51,13 +51,21 @@ struct DecJob {                 // one per session in a decode batch (device arr
     int32_t n_rows;             // Tq
     int32_t offset;             // self-KV length before this call (position of row 0)
     int32_t align_row0;         // first alignment row this call writes (rows accumulated in the epoch)
+    int32_t slot;               // session slot (index of its cross-K/V tensor map)
+    int32_t pad0, pad1, pad2;
 };
 
 void dec_self_attention(const void* q, int type, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model,
                         int n_text_ctx, void* out, cudaStream_t st);
 // align_rank[layer * n_head + head] = rank of the alignment head or -1
 void dec_cross_attention(const void* q, int type, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model,
-                         int n_text_ctx, const int32_t* align_rank, void* out, int max_rows, cudaStream_t st);
+                         int n_text_ctx, const int32_t* align_rank, void* out, int max_rows, bool only_align_heads,
+                         cudaStream_t st);
+// tensor-core prefill path (bf16): every head that is not an alignment head
+void dec_cross_attention_tcgen05(const void* q, int total_rows, const DecJob* jobs, int n_jobs, int max_rows, int layer,
+                                 int n_head, int d_model, const void* kv_maps_dev, const int32_t* align_rank, void* out,
+                                 cudaStream_t st);
+void make_cross_kv_tmap(void* tmap_out_host /* 128 bytes */, const void* cross_kv, int n_layer, int n_head);
 
 struct LogitJob {               // one per session (device array)
     float* logits_last;
@@ -76,6 +84,11 @@ void suppress_tokens(const LogitJob* jobs, int n, const int32_t* tokens_dev, int
 void add_logit_bias(float* logits, const int32_t* tokens_dev, const float* bias_dev, int n, cudaStream_t st);
 void greedy_pick(const LogitJob* jobs, int n, int n_vocab, StepResult* res, cudaStream_t st);
 void align_reduce(const LogitJob* jobs, int n, int n_align, int n_text_ctx, StepResult* res, cudaStream_t st);
+
+// word-timestamp kernels (LocalAgreement path)
+void median_filter(const float* x, float* out, int rows, int cols, int width, cudaStream_t st);
+struct DtwJobHost { const float* x; uint8_t* trace; int32_t* path; int32_t* path_len; int32_t N, M; };
+void dtw_batch(const void* jobs_dev, int n_jobs, int max_tokens, cudaStream_t st);
 
 void convert_f32_to(const float* src, void* dst, int dst_type, int64_t n, cudaStream_t st);
 void convert_to_f32(const void* src, int src_type, float* dst, int64_t n, cudaStream_t st);

@@ -220,6 +220,17 @@ class WhisperEngine:
         be = {"simt": L.BACKEND_SIMT, "tcgen05": L.BACKEND_TCGEN05}[backend]
         L.check(self.lib.wlk_op_encoder_attention(self.h, be, qkv_ptr, dtype_code, batch, out_ptr))
 
+    def op_median_filter(self, x_ptr, out_ptr, rows: int, cols: int, width: int = 7) -> None:
+        L.check(self.lib.wlk_op_median_filter(self.h, x_ptr, out_ptr, rows, cols, width))
+
+    def op_dtw(self, x_ptr, n_tokens: int, n_frames: int):
+        """-> (text_indices, time_indices) like whisper.timing.dtw (reference timing.py:141-151)."""
+        ti = np.zeros(n_tokens + n_frames, np.int32)
+        fi = np.zeros(n_tokens + n_frames, np.int32)
+        n = C.c_int32()
+        L.check(self.lib.wlk_op_dtw(self.h, x_ptr, n_tokens, n_frames, _ptr(ti), _ptr(fi), C.byref(n)))
+        return ti[: n.value].copy(), fi[: n.value].copy()
+
     # -- lifetime ------------------------------------------------------------------------
     def close(self) -> None:
         if not self._closed:
