@@ -49,6 +49,16 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r)
           "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -165,7 +175,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const CUtensorMap* __rest
                 const uint64_t dv = ptx::umma_desc_mnmajor_sw128(sbase + SM_V + s * TILE_BYTES, BKV * 128);
 #pragma unroll
                 for (int k = 0; k < BKV / 16; ++k)             // 16 keys = 16 V rows of 128 B = 2048 B = +128 encoded
-                    umma_bf16_ts(tmem + TM_O, tmem + TM_P + 8 * k, dv + 128 * k, idesc_o, k > 0 ? 1u : 0u);
+                    umma_bf16_ts(tmem + TM_O, tmem + TM_P + 8 * k, dv + 128 * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
                 ptx::umma_commit(bar_o_full);
                 ptx::umma_commit(bar_kv_empty + 8 * s);
             }
@@ -175,111 +185,118 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const CUtensorMap* __rest
         const int qd = warp & 3;
         const int r = qd * 32 + lane;                         // query row within the tile == TMEM lane
         const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-        float acc[DH];
-#pragma unroll
-        for (int e = 0; e < DH; ++e) acc[e] = 0.f;
-        float m = -INFINITY, l = 0.f;                         // running max (log2 domain) and sum
-        // One key tile.  MASKED only for the last tile (92 valid keys of 128): the steady-state path carries
-        // no per-element predicates, exp2 is a bare MUFU.EX2 (ex2.approx.ftz) and the row sum is taken on the
-        // fp32 probabilities -- the profile of the first version was 26 issued instructions per exponential.
+        float m = -INFINITY, l = 0.f;                         // reference max (log2 domain) and running sum
+        // O accumulates in TMEM across key tiles (the P V MMAs run with accumulate on); the softmax threads
+        // only touch it when the row maximum moved by more than 2^8 since the reference maximum `m` was set
+        // (then O and l are rescaled in place).  In between, probabilities are taken against the stale `m`:
+        // they may exceed 1 (by at most 2^8), which bf16 / fp32 hold without loss.  The steady-state tile
+        // carries no per-element predicates (MASKED only for the last, 92-key tile) and exp2 is a bare MUFU.
         auto tile = [&](int j, auto masked_tag) {
             constexpr bool MASKED = decltype(masked_tag)::value;
             const int n_valid = N_CTX - j * BKV;              // only read when MASKED
             ptx::mbar_wait(bar_s_full, j & 1);
             ptx::tc_fence_after();
-            // Both passes walk S in 16-column chunks with the next chunk's tcgen05.ld already in flight
-            // while the current one is consumed (two register buffers): the TMEM read latency sits behind
-            // the max / exp2 work instead of in front of it.
             const uint32_t s_addr = tmem + lane_addr + TM_S;
-            uint32_t va[16], vb[16];
+            uint32_t va[32], vb[32];
+            // ---- pass 1: row maximum (two 32-column loads in flight)
             float mx = -INFINITY;
-            ptx::tmem_ld_32x16(s_addr, va);
-#pragma unroll 1
-            for (int c = 0; c < BKV / 16; c += 2) {
-                ptx::tmem_ld_wait();
-                ptx::tmem_ld_32x16(s_addr + (c + 1) * 16, vb);
+            ptx::tmem_ld_32x32(s_addr, va);
+            ptx::tmem_ld_32x32(s_addr + 32, vb);
+            ptx::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (!MASKED || c * 16 + i < n_valid) mx = fmaxf(mx, __uint_as_float(va[i]));
-                ptx::tmem_ld_wait();
-                if (c + 2 < BKV / 16) ptx::tmem_ld_32x16(s_addr + (c + 2) * 16, va);
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (!MASKED || (c + 1) * 16 + i < n_valid) mx = fmaxf(mx, __uint_as_float(vb[i]));
+            for (int i = 0; i < 32; ++i) {
+                if (!MASKED || i < n_valid) mx = fmaxf(mx, __uint_as_float(va[i]));
+                if (!MASKED || 32 + i < n_valid) mx = fmaxf(mx, __uint_as_float(vb[i]));
             }
-            const float m_new = fmaxf(m, mx * LOG2E);
-            const float alpha = fast_exp2(m - m_new);
-            ptx::tmem_ld_32x16(s_addr, va);                    // first chunk of pass 2 flies during the O update
-            if (j > 0) {                                      // O_{j-1} joins the accumulator before rescaling
-                ptx::mbar_wait(bar_o_full, (j - 1) & 1);
+            ptx::tmem_ld_32x32(s_addr + 64, va);
+            ptx::tmem_ld_32x32(s_addr + 96, vb);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (!MASKED || 64 + i < n_valid) mx = fmaxf(mx, __uint_as_float(va[i]));
+                if (!MASKED || 96 + i < n_valid) mx = fmaxf(mx, __uint_as_float(vb[i]));
+            }
+            const float mx2 = mx * LOG2E;
+            ptx::tmem_ld_32x32(s_addr, va);                    // first chunks of pass 2 fly during the bookkeeping
+            ptx::tmem_ld_32x32(s_addr + 32, vb);
+            // ---- lazy rescale of O / l
+            const bool need = mx2 > m + 8.0f;                  // always true on the first tile (m = -inf)
+            if (j > 0) {
+                ptx::mbar_wait(bar_o_full, (j - 1) & 1);      // P V of the previous tile has landed in O
                 ptx::tc_fence_after();
+                if (__any_sync(0xffffffffu, need)) {           // tcgen05.ld/st are warp-collective
+                    const float alpha = need ? fast_exp2(m - mx2) : 1.0f;
+                    ptx::tmem_ld_wait();                       // (also retires the two S loads above)
+                    uint32_t o[32];
 #pragma unroll
-                for (int c = 0; c < DH / 16; ++c) {
-                    ptx::tmem_ld_32x16(tmem + lane_addr + TM_O + c * 16, vb);
-                    ptx::tmem_ld_wait();
+                    for (int c = 0; c < DH / 32; ++c) {
+                        ptx::tmem_ld_32x32(tmem + lane_addr + TM_O + c * 32, o);
+                        ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) acc[c * 16 + i] = (acc[c * 16 + i] + __uint_as_float(vb[i])) * alpha;
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st_32x32(tmem + lane_addr + TM_O + c * 32, o);
+                    }
+                    ptx::tmem_st_wait();
+                    l *= alpha;
                 }
             }
+            if (need) m = mx2;
+            // ---- pass 2: probabilities against m, row sum, bf16 P back into TMEM
             float rs = 0.f;
-            auto emit = [&](const uint32_t* v, int c) {       // 16 scores -> 16 probabilities -> 8 packed words of P
-                uint32_t pk[8];
+            auto emit = [&](const uint32_t* v, int c) {       // 32 scores -> 16 packed words of P
+                uint32_t pk[16];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), LOG2E, -m_new));
-                    float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, -m_new));
+                for (int i = 0; i < 16; ++i) {
+                    float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), LOG2E, -m));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, -m));
                     if (MASKED) {
-                        if (c * 16 + 2 * i >= n_valid) p0 = 0.f;
-                        if (c * 16 + 2 * i + 1 >= n_valid) p1 = 0.f;
+                        if (c * 32 + 2 * i >= n_valid) p0 = 0.f;
+                        if (c * 32 + 2 * i + 1 >= n_valid) p1 = 0.f;
                     }
                     rs += p0 + p1;
                     __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
                     pk[i] = *reinterpret_cast<uint32_t*>(&hb);
                 }
-                tmem_st_32x8(tmem + lane_addr + TM_P + c * 8, pk);
+                tmem_st_32x16(tmem + lane_addr + TM_P + c * 16, pk);
             };
-#pragma unroll 1
-            for (int c = 0; c < BKV / 16; c += 2) {
-                ptx::tmem_ld_wait();
-                ptx::tmem_ld_32x16(s_addr + (c + 1) * 16, vb);
-                emit(va, c);
-                ptx::tmem_ld_wait();
-                if (c + 2 < BKV / 16) ptx::tmem_ld_32x16(s_addr + (c + 2) * 16, va);
-                emit(vb, c + 1);
-            }
+            ptx::tmem_ld_wait();
+            emit(va, 0);
+            ptx::tmem_ld_32x32(s_addr + 64, va);
+            emit(vb, 1);
+            ptx::tmem_ld_32x32(s_addr + 96, vb);
+            ptx::tmem_ld_wait();
+            emit(va, 2);
+            emit(vb, 3);
             ptx::tmem_st_wait();
-            l = l * alpha + rs;
-            m = m_new;
+            l += rs;
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_s_free);     // S fully consumed: next Q K^T may overwrite it
-            ptx::mbar_arrive(bar_p_full);     // P written, O_{j-1} read: P V may run
+            ptx::mbar_arrive(bar_p_full);     // P written, O rescaled if needed: P V may run
         };
 #pragma unroll 1
         for (int j = 0; j < NT - 1; ++j) tile(j, std::false_type{});
         tile(NT - 1, std::true_type{});
         ptx::mbar_wait(bar_o_full, (NT - 1) & 1);
         ptx::tc_fence_after();
+        const float inv = 1.0f / l;
+        bf16* o = out + (int64_t)(out_row + r) * d_model + h * DH;
 #pragma unroll
         for (int c = 0; c < DH / 32; ++c) {
             uint32_t v[32];
-            ptx::tmem_ld_32x32(tmem + lane_addr + TM_O + c * 32, v);
+            ptx::tmem_ld_32x32(tmem + lane_addr + TM_O + c * 32, v);      // warp-collective: before the row predicate
             ptx::tmem_ld_wait();
+            if (r < n_q) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc[c * 32 + i] += __uint_as_float(v[i]);
-        }
-        if (r < n_q) {
-            const float inv = 1.0f / l;
-            bf16* o = out + (int64_t)(out_row + r) * d_model + h * DH;
-#pragma unroll
-            for (int e8 = 0; e8 < DH / 8; ++e8) {
-                uint4 u;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[e8 * 8 + 0] * inv, acc[e8 * 8 + 1] * inv);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(acc[e8 * 8 + 2] * inv, acc[e8 * 8 + 3] * inv);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[e8 * 8 + 4] * inv, acc[e8 * 8 + 5] * inv);
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(acc[e8 * 8 + 6] * inv, acc[e8 * 8 + 7] * inv);
-                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-                u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-                reinterpret_cast<uint4*>(o)[e8] = u;
+                for (int e8 = 0; e8 < 4; ++e8) {
+                    uint4 u;
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[e8 * 8 + 0]) * inv, __uint_as_float(v[e8 * 8 + 1]) * inv);
+                    __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[e8 * 8 + 2]) * inv, __uint_as_float(v[e8 * 8 + 3]) * inv);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[e8 * 8 + 4]) * inv, __uint_as_float(v[e8 * 8 + 5]) * inv);
+                    __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[e8 * 8 + 6]) * inv, __uint_as_float(v[e8 * 8 + 7]) * inv);
+                    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                    u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+                    reinterpret_cast<uint4*>(o)[c * 4 + e8] = u;
+                }
             }
         }
     }
