@@ -116,7 +116,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("WLK_BENCH_STREAMS", "32")), help="streams per GPU")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("WLK_BENCH_STREAMS", "64")), help="streams per GPU")
     ap.add_argument("--model", default="large-v3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -280,7 +280,7 @@ def main():
             config=dict(workload=workload, model=args.model, streams_per_gpu=B, parallelism=f"sessions sharded x{world}",
                         chunk_s=CHUNK_S, l2="working set (3.4 GB weights + per-stream KV) exceeds the 126 MB L2",
                         rtf_per_stream=(ms_dev / args.steps / 1e3) / CHUNK_S),
-            e2e=dict(value=e2e_value, unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+            e2e=dict(value=e2e_value, unit=unit, h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=d2h * world,
                      ms_per_step=ms_e2e / args.steps),
             gpu_launches=launches,
             clocks=clocks,
