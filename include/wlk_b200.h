@@ -94,6 +94,19 @@ int wlk_encode(wlk_engine* e, const int32_t* sids, int n, int32_t* content_mel_l
  *   the alignment heads' softmaxed cross-attention rows on the device.                    */
 int wlk_decode(wlk_engine* e, const int32_t* sids, int n, const int32_t* tokens, const int32_t* offsets,
                int32_t sot_index);
+/* ---- LocalAgreement path (whisper.transcribe(), reference whisper/transcribe.py:21-497) -------------
+ * wlk_encode_mel: Whisper.encoder(mel) (model.py:238-254) for a log-mel the CALLER computed
+ *   (transcribe.py:122 builds it on the host), mel_host = [n_mels, 3000] fp32; same epoch semantics as
+ *   wlk_encode.
+ * wlk_decode_all_logits: TextDecoder.forward returning the logits of EVERY fed position, as the word-timestamp
+ *   pass needs (whisper/timing.py:197-201); logits_host = [n_tokens, n_vocab] fp32.
+ * wlk_read_align_rows: softmax(qk) rows of the alignment heads accumulated in the current epoch,
+ *   out = [n_align, rows, 1500] fp32 (what the cross-attention hooks of timing.py:186-192 capture).     */
+int wlk_encode_mel(wlk_engine* e, int32_t sid, const float* mel_host, int32_t content_mel_len);
+int wlk_decode_all_logits(wlk_engine* e, int32_t sid, const int32_t* tokens, int n_tokens, int32_t sot_index,
+                          float* logits_host);
+int wlk_read_align_rows(wlk_engine* e, int32_t sid, float* out, int64_t capacity, int32_t* n_align, int32_t* rows);
+
 /* AlignAtt._check_no_speech (simul_whisper.py:370-377)                                     */
 int wlk_no_speech_prob(wlk_engine* e, const int32_t* sids, int n, float* prob_out);
 /* _suppress_blank_tokens / SuppressTokens.apply (simul_whisper.py:379-385, decoding.py:427) */

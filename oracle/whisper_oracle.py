@@ -330,6 +330,34 @@ class OracleEngine:
             s["logits"] = logits[0, -1].clone()
             s["iters"].append(cross)
 
+    # -- LocalAgreement path (whisper.transcribe seam) ------------------------------------
+    @torch.no_grad()
+    def encode_mel(self, sid: int, mel, content_mel_len: int = 1500) -> None:
+        s = self._s[sid]
+        m = _t(np.asarray(mel, np.float32))[None]
+        s["mel"], s["content"] = m, min(1500, int(content_mel_len))
+        s["xa"] = encoder_forward(self.W, self.dims, m)
+        s["kv"], s["iters"], s["logits"], s["sot_row"] = {}, [], None, None
+
+    @torch.no_grad()
+    def decode_all_logits(self, sid: int, tokens: Sequence[int], sot_index: int = 0) -> np.ndarray:
+        s = self._s[sid]
+        t = torch.tensor([list(tokens)], dtype=torch.long)
+        logits, cross = decoder_forward(self.W, self.dims, t, s["xa"], s["kv"])
+        if not s["iters"]:
+            s["sot_row"] = logits[0, sot_index].clone()
+        s["logits"] = logits[0, -1].clone()
+        s["iters"].append(cross)
+        return logits[0].numpy().copy()
+
+    def read_align_rows(self, sid: int) -> np.ndarray:
+        """softmax(qk) rows of the alignment heads over the whole epoch: [n_align, rows, 1500]."""
+        s = self._s[sid]
+        out = []
+        for (l, h) in self.align_heads:
+            out.append(torch.cat([F.softmax(it[l][0, h], dim=-1) for it in s["iters"]], dim=0))
+        return torch.stack(out).numpy()
+
     def no_speech_prob(self, sids: Sequence[int]) -> List[float]:
         return [no_speech_prob(self._s[sid]["sot_row"], self.specials.no_speech) for sid in sids]
 

@@ -190,3 +190,32 @@ def test_bf16_prefill_cross_attention_on_tensor_cores():
     assert np.abs(outs["simt"][0] - ref).max() < 1e-1
     # the alignment rows come from the same (SIMT, exact-softmax) kernel in both configurations
     assert outs["tcgen05"][2][0][2] == outs["simt"][2][0][2]
+
+
+def test_localagreement_entry_points_match_oracle():
+    """wlk_encode_mel / wlk_decode_all_logits / wlk_read_align_rows (the LocalAgreement path's engine calls,
+    see whisperlivekit_b200/localagreement.py) against the CPU oracle, fp32 mode: 1e-3 on logits."""
+    from oracle import whisper_oracle as wo
+    from whisperlivekit_b200.weights import mel_filterbank
+    g, dims, sd, audio, heads = case_setup("tiny")
+    eng = engine_for("tiny", "fp32")
+    orc = wo.OracleEngine(dims, sd, heads)
+    mel, content = wo.encode_features(torch.from_numpy(audio), mel_filterbank(dims.n_mels))
+    mel = mel[0].numpy()
+    toks = list(g["forced_prefix"]) + [int(t) for t in g["forced_steps"]] + [eng.specials.eot]
+    se, so = eng.open_session(), orc.open_session()
+    outs = []
+    for e, s in ((eng, se), (orc, so)):
+        e.encode_mel(s, mel, content)
+        lg = e.decode_all_logits(s, toks, sot_index=0)
+        outs.append((e.read_encoder(s), lg, e.read_align_rows(s)))
+    assert np.abs(outs[0][0] - outs[1][0]).max() < 1e-3
+    assert outs[0][1].shape == (len(toks), dims.n_vocab)
+    assert np.abs(outs[0][1] - outs[1][1]).max() < 1e-3
+    assert outs[0][2].shape == outs[1][2].shape == (len(heads), len(toks), 1500)
+    assert np.abs(outs[0][2] - outs[1][2]).max() < 1e-5
+    # the audio path and the mel path of the engine agree (same mel, computed on device vs on the host)
+    s2 = eng.open_session()
+    eng.append_audio(s2, audio); eng.encode([s2])
+    assert np.abs(eng.read_encoder(s2) - outs[0][0]).max() < 1e-3
+    eng.close_session(se); eng.close_session(s2)

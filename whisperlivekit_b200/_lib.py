@@ -57,6 +57,9 @@ SIGNATURES = {
     "wlk_session_reset_decoder": (C.c_int, [_vp, C.c_int32]),
     "wlk_encode": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "wlk_decode": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int32]),
+    "wlk_encode_mel": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32]),
+    "wlk_decode_all_logits": (C.c_int, [_vp, C.c_int32, _vp, C.c_int, C.c_int32, _vp]),
+    "wlk_read_align_rows": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, _i32p, _i32p]),
     "wlk_no_speech_prob": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "wlk_suppress": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int]),
     "wlk_add_logit_bias": (C.c_int, [_vp, C.c_int32, _vp, _vp, C.c_int]),

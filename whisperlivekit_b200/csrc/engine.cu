@@ -105,6 +105,7 @@ struct wlk_engine {
     cudaEvent_t stg_done = nullptr;
     StepResult *res_dev = nullptr, *res_host = nullptr;
     float* tap_host = nullptr; size_t tap_cap = 0;
+    float* all_logits_dev = nullptr; size_t all_logits_cap = 0;
 
     cudaEvent_t timers[16] = {};
     bool prof_on = false;
@@ -402,10 +403,12 @@ Session& get_session(wlk_engine* e, int32_t sid) {
 // ---------------------------------------------------------------------------------------
 // encode: log-mel -> conv stem -> L encoder blocks -> ln_post -> cross-K/V for every decoder layer
 // ---------------------------------------------------------------------------------------
+void run_encoder(wlk_engine* e, const int32_t* sids, int n, void** xkv_dev);
+
 void encode_batch(wlk_engine* e, const int32_t* sids, int n, int32_t* content_out) {
     const wlk_dims& D = e->dims;
     Weights& W = e->w;
-    const int d = D.n_audio_state, dt = D.n_text_state, nm = D.n_mels;
+    const int nm = D.n_mels;
     const size_t es = e->es();
     WLK_CHECK(n >= 1 && n <= e->cfg.max_batch, "encode batch %d outside [1, %d]", n, e->cfg.max_batch);
     Stager sg(e);
@@ -430,6 +433,15 @@ void encode_batch(wlk_engine* e, const int32_t* sids, int n, int32_t* content_ou
 
     {   ProfScope ps(e, WLK_KC_MEL, 0, (double)n * (480000.0 * 4 + 3000.0 * nm * es));
         mel_forward(mj_dev, n, nm, W.filtT, W.window, W.twiddle, W.filt_span, e->act, e->st); }
+    run_encoder(e, sids, n, xkv_dev);
+}
+
+// conv stem -> L encoder blocks -> ln_post -> cross-K/V, from the time-major mel of `n` streams in e->mel_t
+void run_encoder(wlk_engine* e, const int32_t* sids, int n, void** xkv_dev) {
+    const wlk_dims& D = e->dims;
+    Weights& W = e->w;
+    const int d = D.n_audio_state, dt = D.n_text_state, nm = D.n_mels;
+    const size_t es = e->es();
 
     // conv1 (k=3, pad=1) as a GEMM over overlapping rows of the time-major mel: row t = frames t-1..t+1
     {   GemmArgs g;
@@ -514,7 +526,7 @@ void encode_batch(wlk_engine* e, const int32_t* sids, int n, int32_t* content_ou
 // decode: one TextDecoder.forward over packed rows of several sessions
 // ---------------------------------------------------------------------------------------
 void decode_batch(wlk_engine* e, const int32_t* sids, int n, const int32_t* tokens, const int32_t* offsets,
-                  int32_t sot_index) {
+                  int32_t sot_index, float* all_logits_dev = nullptr) {
     const wlk_dims& D = e->dims;
     Weights& W = e->w;
     const int dt = D.n_text_state, H = D.n_text_head, ctx = D.n_text_ctx;
@@ -611,6 +623,17 @@ void decode_batch(wlk_engine* e, const int32_t* sids, int n, const int32_t* toke
             g.M = R; g.N = dt; g.K = 4 * dt;
             g.epi.bias = L.b2; g.epi.residual = e->dx; g.epi.ldr = dt; g.epi.C = e->dx; g.epi.c_type = DT_F32; g.epi.ldc = dt;
             run_gemm(e, g, WLK_KC_GEMM_DEC); }
+    }
+    if (all_logits_dev) {
+        // word-timestamp pass (find_alignment, timing.py:197-201) reads the logits of EVERY fed position
+        WLK_CHECK(n == 1, "all-logits decode is single-session");
+        {   ProfScope ps(e, WLK_KC_LN);
+            layernorm(e->dx, dt, W.lnw, W.lnb, e->dxn, e->act, dt, R, dt, nullptr, e->st); }
+        GemmArgs g;
+        g.A = e->dxn; g.a_type = e->act; g.lda = dt; g.W = W.emb_act; g.w_type = e->act; g.ldw = dt;
+        g.M = R; g.N = D.n_vocab; g.K = dt;
+        g.epi.C = all_logits_dev; g.epi.c_type = DT_F32; g.epi.ldc = D.n_vocab;
+        run_gemm(e, g, WLK_KC_LOGITS);
     }
     // logits only for the rows the policy reads (last row; sot row on the first call of the epoch)
     {   ProfScope ps(e, WLK_KC_LN);
@@ -776,7 +799,7 @@ void destroy_engine(wlk_engine* e) {
     for (auto& s : e->sess) if (s.open) free_session(e, s);
     void* ptrs[] = {e->arena.base, e->stage_f32, e->mel_t, e->h1, e->x, e->xn, e->qkv, e->att, e->hid, e->audio_scratch, e->mel_scratch,
                     e->pad_rows_dev, e->xptrs_dev, e->dx, e->dxn, e->dq, e->datt, e->dhid, e->dsel, e->stg_dev,
-                    e->res_dev, e->align_rank_dev, e->kv_maps_dev};
+                    e->res_dev, e->align_rank_dev, e->kv_maps_dev, e->all_logits_dev};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->stg_host) cudaFreeHost(e->stg_host);
     if (e->res_host) cudaFreeHost(e->res_host);
@@ -988,6 +1011,56 @@ int wlk_decode(wlk_engine* e, const int32_t* sids, int n, const int32_t* tokens,
     decode_batch(e, sids, n, tokens, offsets, sot_index);
     WLK_API_END
 }
+int wlk_encode_mel(wlk_engine* e, int32_t sid, const float* mel_host, int32_t content_mel_len) {
+    WLK_API_BEGIN
+    LOCK(e);
+    Session& s = get_session(e, sid);
+    WLK_CHECK(mel_host && content_mel_len >= 0, "bad arguments");
+    const int nm = e->dims.n_mels;
+    Stager sg(e);
+    void** xkv_dev; void** xkv = sg.host<void*>(1, &xkv_dev);
+    xkv[0] = s.cross_kv;
+    sg.upload();
+    CUDA_CHECK(cudaMemcpyAsync(e->mel_scratch, mel_host, (size_t)nm * N_FRAMES * 4, cudaMemcpyHostToDevice, e->st));
+    {   ProfScope ps(e, WLK_KC_MEL);
+        mel_import(e->mel_scratch, e->mel_t, e->act, nm, e->st); }
+    run_encoder(e, &sid, 1, xkv_dev);
+    s.content_len = content_mel_len > N_CTX ? N_CTX : content_mel_len;
+    CUDA_CHECK(cudaStreamSynchronize(e->st));        // mel_host may be reused by the caller
+    WLK_API_END
+}
+int wlk_decode_all_logits(wlk_engine* e, int32_t sid, const int32_t* tokens, int n_tokens, int32_t sot_index,
+                          float* logits_host) {
+    WLK_API_BEGIN
+    LOCK(e);
+    WLK_CHECK(tokens && logits_host && n_tokens >= 1 && n_tokens <= e->dims.n_text_ctx, "bad arguments");
+    const size_t need = (size_t)n_tokens * e->dims.n_vocab;
+    if (need > e->all_logits_cap) {
+        if (e->all_logits_dev) CUDA_CHECK(cudaFree(e->all_logits_dev));
+        CUDA_CHECK(cudaMalloc(&e->all_logits_dev, need * 4));
+        e->all_logits_cap = need;
+    }
+    int32_t offs[2] = {0, n_tokens};
+    decode_batch(e, &sid, 1, tokens, offs, sot_index, e->all_logits_dev);
+    CUDA_CHECK(cudaMemcpyAsync(logits_host, e->all_logits_dev, need * 4, cudaMemcpyDeviceToHost, e->st));
+    CUDA_CHECK(cudaStreamSynchronize(e->st));
+    WLK_API_END
+}
+int wlk_read_align_rows(wlk_engine* e, int32_t sid, float* out, int64_t capacity, int32_t* n_align, int32_t* rows) {
+    WLK_API_BEGIN
+    LOCK(e);
+    Session& s = get_session(e, sid);
+    WLK_CHECK(out && n_align && rows, "null argument");
+    const int R = s.align_rows, A = e->n_align;
+    WLK_CHECK((int64_t)A * R * N_CTX <= capacity, "output buffer too small: need %d x %d x %d", A, R, N_CTX);
+    for (int a = 0; a < A; ++a)
+        CUDA_CHECK(cudaMemcpyAsync(out + (size_t)a * R * N_CTX, s.align + (size_t)a * e->dims.n_text_ctx * N_CTX,
+                                   (size_t)R * N_CTX * 4, cudaMemcpyDeviceToHost, e->st));
+    CUDA_CHECK(cudaStreamSynchronize(e->st));
+    *n_align = A; *rows = R;
+    WLK_API_END
+}
+
 int wlk_no_speech_prob(wlk_engine* e, const int32_t* sids, int n, float* prob_out) {
     WLK_API_BEGIN
     LOCK(e);

@@ -177,6 +177,23 @@ void mel_forward(const MelJob* jobs_dev, int batch, int n_mels, const float* fil
     CUDA_CHECK(cudaGetLastError());
 }
 
+// mel computed by the caller (LocalAgreement: whisper.transcribe() builds it on the host) -> the engine's
+// time-major layout with the conv padding rows: out[(f + 1) * n_mels + m] = mel[m * 3000 + f]
+template <typename TO>
+__global__ void mel_import_kernel(const float* __restrict__ mel, TO* __restrict__ out, int n_mels) {
+    const int64_t total = (int64_t)MEL_ROWS * n_mels;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / n_mels), m = (int)(i - (int64_t)r * n_mels);
+        const float v = (r >= 1 && r <= N_FRAMES) ? mel[(int64_t)m * N_FRAMES + (r - 1)] : 0.f;
+        out[i] = from_f32<TO>(v);
+    }
+}
+void mel_import(const float* mel_dev, void* out, int out_type, int n_mels, cudaStream_t st) {
+    if (out_type == DT_F32) mel_import_kernel<float><<<256, 256, 0, st>>>(mel_dev, (float*)out, n_mels);
+    else mel_import_kernel<bf16><<<256, 256, 0, st>>>(mel_dev, (bf16*)out, n_mels);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 // =====================================================================================
 // small utilities
 // =====================================================================================

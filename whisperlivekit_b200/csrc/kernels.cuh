@@ -29,6 +29,8 @@ struct MelJob {                 // one per session in the batch (device array)
 void mel_forward(const MelJob* jobs_dev, int batch, int n_mels, const float* filtT, const float* window,
                  const float2* twiddle, const int2* filt_span, int out_type, cudaStream_t st);
 
+void mel_import(const float* mel_dev /*[n_mels,3000]*/, void* out /*[3002,n_mels]*/, int out_type, int n_mels, cudaStream_t st);
+
 void zero_rows(void* base, int type, int64_t row_elems, const int64_t* row_index_dev, int n_rows, cudaStream_t st);
 
 void layernorm(const float* x, int64_t ldx, const float* w, const float* b, void* out, int out_type, int64_t ldo,

@@ -135,6 +135,25 @@ class WhisperEngine:
         flat = _i32([t for ts in tokens for t in ts])
         L.check(self.lib.wlk_decode(self.h, _ptr(s), len(s), _ptr(flat), _ptr(offs), int(sot_index)))
 
+    # -- LocalAgreement path ---------------------------------------------------------
+    def encode_mel(self, sid: int, mel, content_mel_len: int = 1500) -> None:
+        m = np.ascontiguousarray(np.asarray(mel, dtype=np.float32))
+        assert m.shape == (self.dims.n_mels, 3000), m.shape
+        L.check(self.lib.wlk_encode_mel(self.h, int(sid), _ptr(m), int(content_mel_len)))
+
+    def decode_all_logits(self, sid: int, tokens: Sequence[int], sot_index: int = 0) -> np.ndarray:
+        t = _i32(tokens)
+        out = np.zeros((len(t), self.dims.n_vocab), np.float32)
+        L.check(self.lib.wlk_decode_all_logits(self.h, int(sid), _ptr(t), len(t), int(sot_index), _ptr(out)))
+        return out
+
+    def read_align_rows(self, sid: int) -> np.ndarray:
+        cap = max(1, len(self.align_heads)) * self.dims.n_text_ctx * 1500
+        out = np.zeros(cap, np.float32)
+        a, r = C.c_int32(), C.c_int32()
+        L.check(self.lib.wlk_read_align_rows(self.h, int(sid), _ptr(out), cap, C.byref(a), C.byref(r)))
+        return out[: a.value * r.value * 1500].reshape(a.value, r.value, 1500).copy()
+
     def no_speech_prob(self, sids: Sequence[int]) -> List[float]:
         s = _i32(sids)
         out = np.zeros(len(s), np.float32)

@@ -1,0 +1,227 @@
+"""LocalAgreement seam: a Whisper-shaped model object for the reference's ``whisper.transcribe()``.
+
+The LocalAgreement policy (reference local_agreement/online_asr.py:219-261) calls
+``asr.transcribe(audio, init_prompt)`` -> ``whisper.transcribe(model, audio, ...)``
+(local_agreement/backends.py:62-77), whose host logic (30 s seek loop, temperature fallback,
+timestamp rules, DecodingTask, add_word_timestamps/find_alignment, DTW) stays the reference's.  This
+module supplies the *model*: every tensor operation it is asked for goes to the B200 engine through
+the C ABI.  Needs WhisperLiveKit importable (it reuses the reference's decode/transcribe functions).
+
+What the reference touches on ``model`` (whisper/decoding.py:144-160,636-704; whisper/timing.py:163-215;
+whisper/transcribe.py:111-146) and what answers here:
+    model.dims / device / is_multilingual / num_languages / alignment_heads     -> attributes
+    model.encoder(mel)                         -> wlk_encode_mel, returns an opaque AudioFeatures handle
+    model.decoder(tokens, xa, kv_cache=dict)   -> wlk_decode (+ wlk_read_logits of the rows the caller reads)
+    model.logits(tokens, xa)                   -> decoder without cache
+    model(mel, tokens)                         -> encoder + wlk_decode_all_logits (word-timestamp pass)
+    decoder.blocks[i].cross_attn.register_forward_hook(fn)  -> fn gets log-probabilities of the alignment
+                                                  heads (wlk_read_align_rows): softmax over any frame slice
+                                                  of log p equals the reference's softmax of qk on that slice
+    model.decode / detect_language / transcribe -> the reference's own functions bound to this object
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+
+
+class AudioFeatures:
+    """Opaque stand-in for the encoder output tensor [1, 1500, d] (it never leaves the device)."""
+
+    def __init__(self, model, sid):
+        import torch
+        self.model, self.sid = model, sid
+        self.shape = (1, model.dims.n_audio_ctx, model.dims.n_audio_state)
+        self.dtype = torch.float32
+        self.device = model.device
+        self.ndim = 3
+
+    def __len__(self):
+        return 1
+
+    def __iter__(self):
+        yield self
+
+    def __getitem__(self, key):
+        return self
+
+    def repeat_interleave(self, n, dim=0):
+        if n != 1:
+            raise NotImplementedError("B200 LocalAgreement model: beam search / best_of > 1 not supported yet")
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def half(self):
+        return self
+
+
+class _Hookable:
+    def __init__(self):
+        self.hooks = []
+
+    class _Handle:
+        def __init__(self, owner, fn):
+            self.owner, self.fn = owner, fn
+
+        def remove(self):
+            if self.fn in self.owner.hooks:
+                self.owner.hooks.remove(self.fn)
+
+    def register_forward_hook(self, fn):
+        self.hooks.append(fn)
+        return self._Handle(self, fn)
+
+
+class _Attn(_Hookable):
+    def __init__(self, cache_id):
+        super().__init__()
+        self.key_cache_id = f"{cache_id}_key"
+        self.value_cache_id = f"{cache_id}_value"
+
+
+class _Block:
+    def __init__(self, i):
+        self.attn = _Attn(f"dec_layer{i}_self_attn")
+        self.cross_attn = _Attn(f"dec_layer{i}_cross_attn")
+
+
+class _Decoder:
+    def __init__(self, model):
+        self.model = model
+        self.blocks = [_Block(i) for i in range(model.dims.n_text_layer)]
+
+    def __call__(self, tokens, xa, kv_cache: Optional[dict] = None, return_cross_attn: bool = False):
+        return self.model._decode(tokens, xa, kv_cache)
+
+
+class B200TranscribeModel:
+    """Duck-types the reference ``Whisper`` module for whisper.transcribe()/decode()/find_alignment."""
+
+    def __init__(self, engine):
+        import torch
+        from whisperlivekit.whisper.decoding import decode as decode_function
+        from whisperlivekit.whisper.decoding import detect_language as detect_language_function
+        from whisperlivekit.whisper.transcribe import transcribe as transcribe_function
+        self.engine = engine
+        self.dims = engine.dims
+        self.device = torch.device("cpu")          # host-side tensors (tokens, logits views) live on the CPU
+        self.decoder = _Decoder(self)
+        mask = torch.zeros(self.dims.n_text_layer, self.dims.n_text_head, dtype=torch.bool)
+        for l, h in engine.align_heads:
+            mask[l, h] = True
+        self.alignment_heads = mask.to_sparse()
+        self.sid = engine.open_session()
+        self._decode_fn, self._detect_fn, self._transcribe_fn = decode_function, detect_language_function, transcribe_function
+
+    # -- attributes the reference reads ---------------------------------------------------
+    @property
+    def is_multilingual(self):
+        return self.dims.is_multilingual
+
+    @property
+    def num_languages(self):
+        return self.dims.num_languages
+
+    def decode(self, mel, options=None, **kw):
+        from whisperlivekit.whisper.decoding import DecodingOptions
+        return self._decode_fn(self, mel, options or DecodingOptions(), **kw)
+
+    def detect_language(self, mel, tokenizer=None):
+        return self._detect_fn(self, mel, tokenizer)
+
+    def transcribe(self, audio, **kw):
+        return self._transcribe_fn(self, audio, **kw)
+
+    # -- tensor operations -> engine -------------------------------------------------------
+    def encoder(self, mel):
+        m = mel.detach().cpu().float().numpy()
+        if m.ndim == 3:
+            if m.shape[0] != 1:
+                raise NotImplementedError("B200 LocalAgreement model: one audio segment per call")
+            m = m[0]
+        self.engine.encode_mel(self.sid, m, 1500)
+        return AudioFeatures(self, self.sid)
+
+    embed_audio = encoder
+
+    def _decode(self, tokens, xa, kv_cache):
+        import torch
+        if tokens.shape[0] != 1:
+            raise NotImplementedError("B200 LocalAgreement model: beam search / best_of > 1 not supported yet")
+        toks = [int(t) for t in tokens[0].tolist()]
+        fresh = kv_cache is None or len(kv_cache) == 0
+        if fresh:
+            self.engine.reset_decoder(self.sid)
+            if kv_cache is not None:
+                kv_cache["b200_session"] = self.sid
+        sot = self.engine.specials.sot
+        sot_index = toks.index(sot) if (fresh and sot in toks) else 0
+        self.engine.decode([self.sid], [toks], sot_index=sot_index)
+        logits = torch.zeros(1, len(toks), self.dims.n_vocab)
+        logits[0, -1] = torch.from_numpy(self.engine.read_logits(self.sid))
+        if fresh and len(toks) > 1:
+            logits[0, sot_index] = torch.from_numpy(self.engine.read_sot_logits(self.sid))
+        return logits
+
+    def logits(self, tokens, audio_features, kv_cache=None, return_cross_attn=False):
+        return self._decode(tokens, audio_features, kv_cache)
+
+    def __call__(self, mel, tokens):
+        """Whisper.forward(mel, tokens) (model.py:388-391): used by find_alignment with cross-attn hooks."""
+        import torch
+        self.encoder(mel)
+        toks = [int(t) for t in tokens[0].tolist()]
+        self.engine.reset_decoder(self.sid)
+        all_logits = self.engine.decode_all_logits(self.sid, toks, sot_index=0)
+        hooked = [b for b in self.decoder.blocks if b.cross_attn.hooks]
+        if hooked:
+            rows = self.engine.read_align_rows(self.sid)                 # [n_align, T, 1500] probabilities
+            with np.errstate(divide="ignore"):
+                logp = np.log(rows)
+            per_layer = {}
+            for rank, (l, h) in enumerate(self.engine.align_heads):
+                qk = per_layer.setdefault(l, torch.zeros(1, self.dims.n_text_head, len(toks), 1500))
+                qk[0, h] = torch.from_numpy(logp[rank])
+            for i, b in enumerate(self.decoder.blocks):
+                qk = per_layer.get(i)
+                if qk is None:
+                    qk = torch.zeros(1, self.dims.n_text_head, len(toks), 1500)
+                for fn in list(b.cross_attn.hooks):
+                    fn(b.cross_attn, (), (None, qk))
+        return torch.from_numpy(all_logits)[None]
+
+    def close(self):
+        self.engine.close_session(self.sid)
+
+
+class B200WhisperASR:
+    """Mirror of the reference's ``WhisperASR`` (local_agreement/backends.py:39-99) over B200TranscribeModel:
+    same ``transcribe / ts_words / segments_end_ts / use_vad`` duck-type that ``OnlineASRProcessor`` drives."""
+    sep = " "
+
+    def __init__(self, engine, lan: str = "en"):
+        self.model = B200TranscribeModel(engine)
+        self.original_language = None if lan == "auto" else lan
+        self.transcribe_kargs = {}
+
+    def transcribe(self, audio, init_prompt=""):
+        options = dict(self.transcribe_kargs)
+        options.pop("vad", None)
+        options.pop("vad_filter", None)
+        language = self.original_language if self.original_language else None
+        return self.model.transcribe(audio, language=language, initial_prompt=init_prompt,
+                                     condition_on_previous_text=True, word_timestamps=True, **options)
+
+    def ts_words(self, r):
+        from whisperlivekit.timed_objects import ASRToken
+        return [ASRToken(w["start"], w["end"], w["word"], probability=w.get("probability"))
+                for seg in r["segments"] for w in seg["words"]]
+
+    def segments_end_ts(self, res) -> List[float]:
+        return [seg["end"] for seg in res["segments"]]
+
+    def use_vad(self):
+        pass
