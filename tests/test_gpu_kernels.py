@@ -52,7 +52,8 @@ def test_gemm_simt_fp32(eng, M, N, K, gelu):
 
 
 SHAPES_TC = [(128, 256, 64), (256, 256, 128), (1500, 1280, 1280), (3000, 384, 240), (1000, 3840, 1280),
-             (129, 264, 72), (64, 128, 5120), (4500, 5120, 1280), (12000, 1280, 5120)]
+             (129, 264, 72), (64, 128, 5120), (4500, 5120, 1280), (12000, 1280, 5120),
+             (16, 3840, 1280), (64, 1280, 1280), (1, 51864, 384), (200, 1280, 5120)]
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES_TC)

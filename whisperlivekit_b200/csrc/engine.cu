@@ -586,7 +586,7 @@ void decode_batch(wlk_engine* e, const int32_t* sids, int n, const int32_t* toke
             g.epi.layer = li; g.epi.n_head = H; g.epi.d_model = dt; g.epi.kv_len = ctx;
             run_gemm(e, g, WLK_KC_GEMM_DEC); }
         {   ProfScope ps(e, WLK_KC_ATTN_DEC_SELF);
-            dec_self_attention(e->dq, e->act, dj_dev, n, li, H, dt, ctx, e->datt, e->st); }
+            dec_self_attention(e->dq, e->act, dj_dev, n, li, H, dt, ctx, e->datt, max_tq, e->st); }
         {   GemmArgs g;
             g.A = e->datt; g.a_type = e->act; g.lda = dt; g.W = L.Wo; g.w_type = e->act; g.ldw = dt;
             g.M = R; g.N = dt; g.K = dt;

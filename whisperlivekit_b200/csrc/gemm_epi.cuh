@@ -34,7 +34,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // the scatter modes -- was computed once per tile (`row`), and the column part once per chunk (epi_col).
 __device__ __forceinline__ void epilogue_warp_tile(const Epilogue& epi, float* sbias, const EpiRow& row,
                                                    uint32_t tmem_row_addr, int n_tile_base, int col_begin, int n_chunks,
-                                                   int N, int lane, bool split_k = false, bool first_split = true) {
+                                                   int N, int lane, const float* partials = nullptr, int splits = 1,
+                                                   int own_split = 0, int64_t split_stride = 0, int tile_ld = 0) {
     const int es = (epi.c_type == DT_F32) ? 4 : 2;
     // bias of this warp's columns -> smem (each lane 4 floats), read back as broadcasts
     if (epi.bias) {
@@ -62,14 +63,18 @@ __device__ __forceinline__ void epilogue_warp_tile(const Epilogue& epi, float* s
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-        if (split_k) {
-            // partial sum of one K range: accumulate into the fp32 residual stream in place
-            float* o = reinterpret_cast<float*>(p);
+        if (partials) {
+            // split-K fix-up: this CTA arrived last at the tile; fold in the other K ranges' partial sums
+            // (fp32, [split][128 rows][tile_ld cols] in global scratch; `partials` already points at this row)
+            for (int sp = 0; sp < splits; ++sp) {
+                if (sp == own_split) continue;
+                const float4* pp = reinterpret_cast<const float4*>(partials + sp * split_stride + c0);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                if (n0 + j < N) atomicAdd(o + j, v[j] + ((first_split && epi.bias) ? sbias[c * 16 + j] : 0.f));
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 b = __ldcg(pp + j4);
+                    v[4 * j4] += b.x; v[4 * j4 + 1] += b.y; v[4 * j4 + 2] += b.z; v[4 * j4 + 3] += b.w;
+                }
             }
-            continue;
         }
         if (epi.bias) {
 #pragma unroll
@@ -140,6 +145,27 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int ban
     const int h = min(band, num_m - b * band);       // height of this (possibly last, shorter) band
     *n_blk = r / h;
     *m_blk = b * band + (r - (*n_blk) * h);
+}
+
+// split-K, phase 1: dump this K range's raw accumulators of the warp's rows/columns to the global scratch
+__device__ __forceinline__ void epilogue_store_partials(float* dst_row /* scratch row of this thread */, bool row_valid,
+                                                        uint32_t tmem_row_addr, int col_begin, int n_chunks) {
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; ++c) {
+        const int c0 = col_begin + c * 16;
+        uint32_t r[16];
+        __syncwarp();
+        ptx::tmem_ld_32x16(tmem_row_addr + c0, r);
+        ptx::tmem_ld_wait();
+        if (row_valid) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+                __stcg(reinterpret_cast<float4*>(dst_row + c0) + j4,
+                       make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]), __uint_as_float(r[4 * j4 + 2]),
+                                   __uint_as_float(r[4 * j4 + 3])));
+        }
+    }
+    __syncwarp();
 }
 
 bool make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,

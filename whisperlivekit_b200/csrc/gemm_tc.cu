@@ -70,7 +70,7 @@ struct SmemLayout {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M, int N, int K,
-               int splits, Epilogue epi) {
+               int splits, float* __restrict__ sk_scratch, int* __restrict__ sk_counters, Epilogue epi) {
     using L = SmemLayout<BN, STAGES>;
     constexpr uint32_t TMEM_COLS = 2 * BN;           // 128 / 256 / 512: powers of two >= 32
     extern __shared__ uint8_t smem_raw[];
@@ -170,6 +170,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;                       // TMEM lane quadrant this warp may access
         const int hc = ew >> 2;                       // which half of the tile's columns
         float* sbias = reinterpret_cast<float*>(smem_gen + L::STG_OFF) + ew * EPI_BIAS_FLOATS;
+        volatile int* sk_flag = reinterpret_cast<volatile int*>(smem_gen + (tmem_slot - smem_base) + 8);
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int sp = tile / num_mn, mn = tile - sp * num_mn;
@@ -179,8 +180,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const EpiRow row = epi_row(epi, m_blk * BM + q * 32 + lane, M);
             ptx::mbar_wait(bar_tfull + 8 * as, ap);
             ptx::tc_fence_after();
-            epilogue_warp_tile(epi, sbias, row, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN,
-                               n_blk * BN, hc * (BN / 2), BN / 32, N, lane, splits > 1, sp == 0);
+            const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+            if (splits > 1) {
+                // Split-K with a serial fix-up: every CTA of a tile parks its raw partial sums in global scratch;
+                // the one that arrives last (atomic ticket) adds the others to its own accumulators and runs the
+                // normal fused epilogue, so any output type / scatter mode works.
+                const int64_t split_stride = (int64_t)num_mn * BM * BN;
+                float* my_row = sk_scratch + ((int64_t)sp * num_mn + mn) * BM * BN + (int64_t)(q * 32 + lane) * BN;
+                const bool row_valid = (m_blk * BM + q * 32 + lane) < M;
+                epilogue_store_partials(my_row, row_valid, tacc, hc * (BN / 2), BN / 32);
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+                if (ew == 0 && lane == 0) {
+                    const int old = atomicAdd(sk_counters + mn, 1);
+                    const int last = (old == splits - 1);
+                    if (last) sk_counters[mn] = 0;                    // every split has arrived: re-arm for the next launch
+                    *sk_flag = last;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+                const int last = *sk_flag;
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");   // flag may be rewritten next tile
+                if (last) {
+                    __threadfence();
+                    const float* base_row = sk_scratch + (int64_t)mn * BM * BN + (int64_t)(q * 32 + lane) * BN;
+                    epilogue_warp_tile(epi, sbias, row, tacc, n_blk * BN, hc * (BN / 2), BN / 32, N, lane,
+                                       base_row, splits, sp, split_stride, BN);
+                }
+            } else {
+                epilogue_warp_tile(epi, sbias, row, tacc, n_blk * BN, hc * (BN / 2), BN / 32, N, lane);
+            }
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_tempty + 8 * as);
         }
@@ -191,9 +219,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// split-K scratch: fp32 partial tiles + one arrival counter per output tile (zero between launches)
+static float* g_sk_scratch = nullptr;
+static int* g_sk_counters = nullptr;
+constexpr size_t SK_SCRATCH_FLOATS = (size_t)8 << 20;     // 32 MB
+constexpr int SK_MAX_TILES = 4096;
+
 template <int BN, int STAGES>
 void launch(const GemmArgs& g, cudaStream_t st, int num_sms, int splits = 1) {
     using L = SmemLayout<BN, STAGES>;
+    if (splits > 1) {
+        const int tiles_mn = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+        if ((size_t)splits * tiles_mn * BM * BN > SK_SCRATCH_FLOATS || tiles_mn > SK_MAX_TILES) splits = 1;
+        else if (!g_sk_scratch) {
+            CUDA_CHECK(cudaMalloc(&g_sk_scratch, SK_SCRATCH_FLOATS * 4));
+            CUDA_CHECK(cudaMalloc(&g_sk_counters, SK_MAX_TILES * 4));
+            CUDA_CHECK(cudaMemset(g_sk_counters, 0, SK_MAX_TILES * 4));
+        }
+    }
     CUtensorMap tmA, tmW;
     std::string err;
     WLK_CHECK(make_tmap_bf16_2d(&tmA, g.A, g.M, g.K, g.lda, BM, BK, &err), "A tensor map: %s", err.c_str());
@@ -206,7 +249,7 @@ void launch(const GemmArgs& g, cudaStream_t st, int num_sms, int splits = 1) {
     }
     const int num_tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * splits;
     const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-    gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, L::DYN, st>>>(tmA, tmW, g.M, g.N, g.K, splits, g.epi);
+    gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, L::DYN, st>>>(tmA, tmW, g.M, g.N, g.K, splits, g_sk_scratch, g_sk_counters, g.epi);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -238,24 +281,22 @@ void gemm_tcgen05(const GemmArgs& g, cudaStream_t st, int num_sms, int variant) 
     if (g.N >= 256 && tiles256 >= num_sms) launch<256, 4>(g, st, num_sms);
     else if (g.N >= 128 && ((g.M + BM - 1) / BM) * ((g.N + 127) / 128) >= num_sms / 2) launch<128, 6>(g, st, num_sms);
     else {
-        // Short, narrow problems (the decoder's per-token GEMMs) cannot fill the GPU with output tiles alone.
-        // When the output is the fp32 residual stream updated in place (x += A W^T + b), the K range is split
-        // across CTAs that accumulate with fp32 atomics (the first split carries the bias).
+        // Short, narrow problems (the decoder's per-token GEMMs) cannot fill the GPU with output tiles alone and
+        // a CTA walking all of K pays one TMA round trip per ring refill.  The K range is split across CTAs
+        // (serial fix-up in the epilogue, see gemm_tc_kernel) until the grid covers the SMs.
+        const int tiles64 = ((g.M + BM - 1) / BM) * ((g.N + 63) / 64);
+        const int num_k = (g.K + BK - 1) / BK;
         int splits = 1;
-        const int tiles = ((g.M + BM - 1) / BM) * ((g.N + 63) / 64);
-        const bool in_place = g.epi.mode == EPI_PLAIN && g.epi.c_type == DT_F32 && g.epi.residual == g.epi.C &&
-                              g.epi.C != nullptr && !g.epi.gelu && g.epi.scale_cols == 0;
-        if (in_place && tiles * 2 <= num_sms) {
-            const int num_k = (g.K + BK - 1) / BK;
-            splits = num_sms / tiles;
-            if (splits > num_k / 4) splits = num_k / 4;       // at least 4 k-slabs per split
+        // (measured: the fix-up costs ~6 us, a ring refill ~2.4 us -- it pays from ~40 k-slabs, i.e. K = 5120)
+        if (tiles64 < num_sms && num_k >= 40) {
+            splits = num_sms / tiles64;
+            if (splits > num_k / 8) splits = num_k / 8;       // at least one full ring (8 k-slabs) per split
             if (splits > 8) splits = 8;
             if (splits < 1) splits = 1;
             const int kbps = (num_k + splits - 1) / splits;
             splits = (num_k + kbps - 1) / kbps;               // no empty K range
         }
-        if (splits == 1 && tiles * 2 <= num_sms && g.N >= 64) launch<32, 8>(g, st, num_sms);   // more, narrower tiles
-        else launch<64, 8>(g, st, num_sms, splits);
+        launch<64, 8>(g, st, num_sms, splits);
     }
 }
 

@@ -10,7 +10,7 @@
 //                                       on the leader's "full" barrier
 //   warp 1  MMA issuer (leader only)  : tcgen05.mma.cta_group::2.kind::f16; tcgen05.commit...multicast frees
 //                                       the smem slot in both CTAs and publishes the accumulator to both
-//   warps 2..9 epilogue (both CTAs)   : same fused epilogue as the 1-CTA kernel on the CTA's own 128 rows;
+//   warps 2..17 epilogue (both CTAs)   : same fused epilogue as the 1-CTA kernel on the CTA's own 128 rows;
 //                                       "accumulator drained" arrives (remotely for the peer) on the leader
 #include <cudaTypedefs.h>
 
@@ -23,7 +23,7 @@ constexpr int BM2 = 256;          // rows per cluster tile (128 per CTA)
 constexpr int BN2 = 256;          // columns per cluster tile (each CTA stages 128 rows of W)
 constexpr int BK2 = 64;
 constexpr int STAGES2 = 6;
-constexpr int NUM_EPI_WARPS2 = 8;
+constexpr int NUM_EPI_WARPS2 = 16;      // 4 per TMEM lane quadrant, each draining a quarter of the tile's columns
 constexpr int NUM_THREADS2 = 64 + 32 * NUM_EPI_WARPS2;
 constexpr uint32_t A_BYTES2 = 128 * BK2 * 2;     // 16 KB
 constexpr uint32_t B_BYTES2 = 128 * BK2 * 2;     // 16 KB
@@ -177,7 +177,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // ===================== epilogue (both CTAs, own 128 rows) =====================
         const int ew = warp - 2;
         const int q = warp & 3;
-        const int hc = ew >> 2;
+        const int hc = ew >> 2;                                       // which quarter of the columns
+        constexpr int COLS_PER_WARP = BN2 / (NUM_EPI_WARPS2 / 4);
         float* sbias = reinterpret_cast<float*>(smem_gen + STG_OFF2) + ew * EPI_BIAS_FLOATS;
         uint32_t it = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
@@ -188,7 +189,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             ptx::mbar_wait(bar_tfull + 8 * as, ap);
             ptx::tc_fence_after();
             epilogue_warp_tile(epi, sbias, row, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN2,
-                               n_blk * BN2, hc * (BN2 / 2), BN2 / 32, N, lane);
+                               n_blk * BN2, hc * COLS_PER_WARP, COLS_PER_WARP / 16, N, lane);
             ptx::tc_fence_before();
             mbar_arrive_cta(bar_tempty + 8 * as, 0);
         }

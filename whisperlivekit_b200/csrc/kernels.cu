@@ -491,18 +491,18 @@ template <> struct RowVec<float> {
 // One warp per query row (8 queries in flight per CTA), no block-level synchronisation: lanes own keys
 // lane, lane+32, ... for the scores (whole 64-wide K rows per lane, 128-bit loads), softmax by warp shuffles,
 // then lanes own two output dims each and walk the keys with the probabilities broadcast by shuffle.
-template <typename T>
-__global__ void __launch_bounds__(256)
+template <typename T, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 dec_self_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, int layer, int n_head, int d_model,
                      int n_text_ctx, T* __restrict__ out) {
     constexpr int MAXK = 14;                 // ceil(448 / 32) keys per lane
     constexpr int VN = RowVec<T>::N;
-    __shared__ float qs[8][64];
+    __shared__ float qs[WARPS][64];
     const DecJob job = jobs[blockIdx.y];
     const int h = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const T* Kc = reinterpret_cast<const T*>(job.self_kv) + (((int64_t)layer * 2 + 0) * n_head + h) * n_text_ctx * 64;
     const T* Vc = reinterpret_cast<const T*>(job.self_kv) + (((int64_t)layer * 2 + 1) * n_head + h) * n_text_ctx * 64;
-    for (int t = warp; t < job.n_rows; t += 8) {
+    for (int t = warp; t < job.n_rows; t += WARPS) {
         const int64_t row = job.row_off + t;
         const int n_keys = job.offset + t + 1;            // causal: keys 0 .. position
         qs[warp][lane] = to_f32(q[row * d_model + h * 64 + lane]);
@@ -542,11 +542,22 @@ dec_self_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, i
         for (int i = 0; i < MAXK; ++i) {
             if (32 * i >= n_keys) break;                   // warp-uniform
             const int lim = min(32, n_keys - 32 * i);
-            for (int l = 0; l < lim; ++l) {
-                const float p = __shfl_sync(0xffffffffu, sc[i], l);
-                const T* vr = Vc + (int64_t)(32 * i + l) * 64 + 2 * lane;
-                o0 = fmaf(p, to_f32(vr[0]), o0);
-                o1 = fmaf(p, to_f32(vr[1]), o1);
+            // 16 V rows are fetched before any is used: a serial walk would expose one global-load latency per key
+            for (int l0 = 0; l0 < lim; l0 += 16) {
+                float v0[16], v1[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int key = 32 * i + min(l0 + u, lim - 1);
+                    const T* vr = Vc + (int64_t)key * 64 + 2 * lane;
+                    v0[u] = to_f32(vr[0]);
+                    v1[u] = to_f32(vr[1]);
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const float p = (l0 + u < lim) ? __shfl_sync(0xffffffffu, sc[i], (l0 + u) & 31) : 0.f;
+                    o0 = fmaf(p, v0[u], o0);
+                    o1 = fmaf(p, v1[u], o1);
+                }
             }
         }
         const float inv = 1.0f / sum;
@@ -556,11 +567,16 @@ dec_self_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, i
     }
 }
 void dec_self_attention(const void* q, int type, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model,
-                        int n_text_ctx, void* out, cudaStream_t st) {
+                        int n_text_ctx, void* out, int max_rows, cudaStream_t st) {
     WLK_CHECK(n_text_ctx <= 448, "dec_self_attention: n_text_ctx %d > 448", n_text_ctx);
     dim3 grid(n_head, n_jobs);
-    if (type == DT_F32) dec_self_attn_kernel<float><<<grid, 256, 0, st>>>((const float*)q, jobs, layer, n_head, d_model, n_text_ctx, (float*)out);
-    else dec_self_attn_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)q, jobs, layer, n_head, d_model, n_text_ctx, (bf16*)out);
+    if (max_rows <= 1) {                      // token step: one warp per (session, head), a single wave of tiny CTAs
+        if (type == DT_F32) dec_self_attn_kernel<float, 1><<<grid, 32, 0, st>>>((const float*)q, jobs, layer, n_head, d_model, n_text_ctx, (float*)out);
+        else dec_self_attn_kernel<bf16, 1><<<grid, 32, 0, st>>>((const bf16*)q, jobs, layer, n_head, d_model, n_text_ctx, (bf16*)out);
+    } else {
+        if (type == DT_F32) dec_self_attn_kernel<float, 8><<<grid, 256, 0, st>>>((const float*)q, jobs, layer, n_head, d_model, n_text_ctx, (float*)out);
+        else dec_self_attn_kernel<bf16, 8><<<grid, 256, 0, st>>>((const bf16*)q, jobs, layer, n_head, d_model, n_text_ctx, (bf16*)out);
+    }
     CUDA_CHECK(cudaGetLastError());
 }
 

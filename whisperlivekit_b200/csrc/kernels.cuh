@@ -58,7 +58,7 @@ struct DecJob {                 // one per session in a decode batch (device arr
 };
 
 void dec_self_attention(const void* q, int type, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model,
-                        int n_text_ctx, void* out, cudaStream_t st);
+                        int n_text_ctx, void* out, int max_rows, cudaStream_t st);
 // align_rank[layer * n_head + head] = rank of the alignment head or -1
 void dec_cross_attention(const void* q, int type, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model,
                          int n_text_ctx, const int32_t* align_rank, void* out, int max_rows, bool only_align_heads,
