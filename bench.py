@@ -116,7 +116,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("WLK_BENCH_STREAMS", "64")), help="streams per GPU")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("WLK_BENCH_STREAMS", "96")), help="streams per GPU")
     ap.add_argument("--model", default="large-v3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
