@@ -198,6 +198,8 @@ def main():
     h2d = B * CHUNK * 4
     d2h = B * 16 * (STEPS_PER_CHUNK + 1)                     # StepResult per stream per sync
 
+    host = dict(encode=0.0, prefill=0.0, step=0.0, n=0)      # host-side enqueue time of the engine calls (no sync inside)
+
     def step(with_io: bool, k: int):
         if with_io:
             chunk_host.copy_(torch.from_numpy(0.05 * rng.standard_normal((B, CHUNK)).astype(np.float32)))
@@ -205,13 +207,19 @@ def main():
             for i, s in enumerate(sids):
                 eng.drop_audio(s, CHUNK)
                 eng.append_audio(s, cn[i])
+        t0 = time.perf_counter()
         eng.encode(sids)
+        t1 = time.perf_counter()
         eng.decode(sids, [prefix] * B)
+        t2 = time.perf_counter()
+        host["encode"] += t1 - t0; host["prefill"] += t2 - t1; host["n"] += 1
         eng.no_speech_prob(sids)
         for _ in range(STEPS_PER_CHUNK):
             eng.suppress(sids, sup)
             r = eng.greedy_and_align(sids)
+            t3 = time.perf_counter()
             eng.decode(sids, [[t[0]] for t in r])
+            host["step"] += time.perf_counter() - t3
 
     def timed(with_io: bool, steps: int, warmup: int, profile: bool):
         for k in range(warmup):
@@ -290,6 +298,9 @@ def main():
                           flops_per_launch=g["flops"] / max(1, g["launches"]), ms_per_launch=g["ms"] / max(1, g["launches"])),
             kernel_classes=classes,
             profiled_ms_per_step=ms_prof / args.steps,
+            host_enqueue_ms=dict(encode_call=1e3 * host["encode"] / host["n"], prefill_call=1e3 * host["prefill"] / host["n"],
+                                 decode_step_call=1e3 * host["step"] / host["n"] / STEPS_PER_CHUNK,
+                                 note="host time inside the (asynchronous) engine calls, averaged over all passes"),
         )
         if not args.no_cpu_baseline:
             sd_cpu = sd if world == 1 or rank == 0 else None

@@ -9,10 +9,11 @@
 //   warp 1     MMA issuer   : S = Q K^T   (tcgen05.mma SS, M128 N128 K16 x4)      -> TMEM cols [0,128)
 //                             O_j = P V   (tcgen05.mma TS: P from TMEM, V MN-major smem, N64, K16 x8)
 //                                                                                  -> TMEM cols [128,192)
-//   warps 2-5  softmax      : thread = query row. tcgen05.ld S in 32-column chunks (two passes: row max,
-//                             then exp2 / row sum), P packed to bf16 and written back to TMEM
-//                             (cols [192,256)) with tcgen05.st, running O kept in registers and rescaled
-//                             online; final O / l stored as bf16.
+//   warps 2-9  softmax      : two threads per query row (64 keys of the tile each). tcgen05.ld S in 16-column
+//                             chunks, ONE pass: exp2 against the row's reference maximum, row sum, and the
+//                             tile's true maximum on the side; P packed to bf16 and written back to TMEM
+//                             (cols [192,256)) with tcgen05.st.  O stays in TMEM across key tiles and is only
+//                             rescaled when the reference maximum has to move (rare); final O / l as bf16.
 #include <cudaTypedefs.h>
 
 #include <type_traits>
@@ -28,10 +29,11 @@ bool make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t
 namespace {
 
 constexpr int BQ = 128, BKV = 128, DH = 64;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;          // TMA warp, MMA warp, 8 softmax warps
 constexpr uint32_t TILE_BYTES = BQ * DH * 2;          // 16 KB: Q, K and V tiles all are 128 x 64 bf16
 constexpr uint32_t SM_Q = 0, SM_K = TILE_BYTES, SM_V = 3 * TILE_BYTES, SM_BAR = 5 * TILE_BYTES;
-constexpr uint32_t ATT_SMEM = SM_BAR + 128 + 1024;
+constexpr uint32_t SM_XCH = SM_BAR + 128;             // row-half exchange: [2][2][128] floats
+constexpr uint32_t ATT_SMEM = SM_XCH + 2 * 2 * BQ * 4 + 1024;
 constexpr uint32_t TM_S = 0, TM_O = 128, TM_P = 192, TM_COLS = 256;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -99,6 +101,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const CUtensorMap* __rest
     const uint32_t tmem_slot = bar_q + 72;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sgen + SM_BAR + 72);
 
+    ptx::griddep_launch();                   // programmatic dependent launch: see launch_pdl (common.cuh)
+    ptx::griddep_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
     constexpr int NT = (N_CTX + BKV - 1) / BKV;          // 12 key tiles
@@ -128,8 +132,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const CUtensorMap* __rest
         ptx::mbar_init(bar_q, 1);
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_kv_full + 8 * i, 1); ptx::mbar_init(bar_kv_empty + 8 * i, 1); }
         ptx::mbar_init(bar_s_full, 1);
-        ptx::mbar_init(bar_s_free, 128);
-        ptx::mbar_init(bar_p_full, 128);
+        ptx::mbar_init(bar_s_free, 256);
+        ptx::mbar_init(bar_p_full, 256);
         ptx::mbar_init(bar_o_full, 1);
         ptx::fence_barrier_init();
     }
@@ -182,93 +186,110 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const CUtensorMap* __rest
             __syncwarp();
         }
     } else {
+        // ---- softmax: two threads per query row (warps w and w+4 share a TMEM lane quadrant; each owns 64 of
+        // the tile's 128 keys), eight warps per CTA, sixteen per SM: enough warps per scheduler to cover the
+        // tcgen05.ld round trips with other rows' exponentials.
         const int qd = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int r = qd * 32 + lane;                         // query row within the tile == TMEM lane
         const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-        float m = -INFINITY, l = 0.f;                         // reference max (log2 domain) and running sum
-        // O accumulates in TMEM across key tiles (the P V MMAs run with accumulate on); the softmax threads
-        // only touch it when the row maximum moved by more than 2^8 since the reference maximum `m` was set
-        // (then O and l are rescaled in place).  In between, probabilities are taken against the stale `m`:
-        // they may exceed 1 (by at most 2^8), which bf16 / fp32 hold without loss.  The steady-state tile
-        // carries no per-element predicates (MASKED only for the last, 92-key tile) and exp2 is a bare MUFU.
+        const uint32_t s_addr = tmem + lane_addr + TM_S + half * (BKV / 2);
+        const uint32_t p_addr = tmem + lane_addr + TM_P + half * (BKV / 4);
+        const uint32_t o_addr = tmem + lane_addr + TM_O + half * (DH / 2);
+        float* xch = reinterpret_cast<float*>(sgen + SM_XCH);  // [2 parities][2 halves][128 rows]
+        uint32_t xn = 0;
+        // combine a per-thread value with the row's other half (named barrier of the two warps of a quadrant)
+        auto exchange = [&](float v) -> float {
+            float* slot = xch + (xn & 1) * 2 * BQ;
+            ++xn;
+            slot[half * BQ + r] = v;
+            switch (qd) {                                      // literal ids: ptxas then reserves 5 barriers, not all 16
+                case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+                case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+                case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+                default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+            }
+            return slot[(half ^ 1) * BQ + r];
+        };
+        float m = -INFINITY, l = 0.f;                         // reference max (log2 domain), this half's running sum
+        // One pass per key tile.  Probabilities are taken against the row's reference maximum `m`, which is
+        // only moved (and O, l rescaled in place in TMEM) when a tile's true maximum -- found during the same
+        // pass -- exceeds it by more than 2^8; in that rare case the tile's probabilities are recomputed
+        // against the new reference before anything consumes them.  Until then values may exceed 1 by at most
+        // 2^8, which bf16 / fp32 hold without loss.  The steady-state tile has no per-element predicates
+        // (MASKED only for the last, 92-key tile) and exp2 is a bare MUFU.
         auto tile = [&](int j, auto masked_tag) {
             constexpr bool MASKED = decltype(masked_tag)::value;
-            const int n_valid = N_CTX - j * BKV;              // only read when MASKED
+            const int n_valid = N_CTX - j * BKV - half * (BKV / 2);   // valid keys in this thread's 64 (MASKED only)
             ptx::mbar_wait(bar_s_full, j & 1);
-            ptx::tc_fence_after();
-            const uint32_t s_addr = tmem + lane_addr + TM_S;
-            uint32_t va[32], vb[32];
-            // ---- pass 1: row maximum (two 32-column loads in flight)
-            float mx = -INFINITY;
-            ptx::tmem_ld_32x32(s_addr, va);
-            ptx::tmem_ld_32x32(s_addr + 32, vb);
-            ptx::tmem_ld_wait();
+            ptx::tc_fence_after();                            // (Q K^T of tile j retired => P V of tile j-1 did too)
+            uint32_t va[16], vb[16];
+            if (j == 0) {                                     // first tile: a true row maximum seeds the reference
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < 4; c += 2) {
+                    ptx::tmem_ld_32x16(s_addr + c * 16, va);
+                    ptx::tmem_ld_32x16(s_addr + c * 16 + 16, vb);
+                    ptx::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                if (!MASKED || i < n_valid) mx = fmaxf(mx, __uint_as_float(va[i]));
-                if (!MASKED || 32 + i < n_valid) mx = fmaxf(mx, __uint_as_float(vb[i]));
+                    for (int i = 0; i < 16; ++i) {
+                        if (!MASKED || c * 16 + i < n_valid) mx = fmaxf(mx, __uint_as_float(va[i]));
+                        if (!MASKED || c * 16 + 16 + i < n_valid) mx = fmaxf(mx, __uint_as_float(vb[i]));
+                    }
+                }
+                m = fmaxf(mx, exchange(mx)) * LOG2E;
             }
-            ptx::tmem_ld_32x32(s_addr + 64, va);
-            ptx::tmem_ld_32x32(s_addr + 96, vb);
-            ptx::tmem_ld_wait();
+#pragma unroll 1
+            for (;;) {
+                float rs = 0.f, mx = -INFINITY;
+                auto emit = [&](const uint32_t* v, int c) {   // 16 scores -> 8 packed words of P
+                    uint32_t pk[8];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                if (!MASKED || 64 + i < n_valid) mx = fmaxf(mx, __uint_as_float(va[i]));
-                if (!MASKED || 96 + i < n_valid) mx = fmaxf(mx, __uint_as_float(vb[i]));
-            }
-            const float mx2 = mx * LOG2E;
-            ptx::tmem_ld_32x32(s_addr, va);                    // first chunks of pass 2 fly during the bookkeeping
-            ptx::tmem_ld_32x32(s_addr + 32, vb);
-            // ---- lazy rescale of O / l
-            const bool need = mx2 > m + 8.0f;                  // always true on the first tile (m = -inf)
-            if (j > 0) {
-                ptx::mbar_wait(bar_o_full, (j - 1) & 1);      // P V of the previous tile has landed in O
-                ptx::tc_fence_after();
-                if (__any_sync(0xffffffffu, need)) {           // tcgen05.ld/st are warp-collective
-                    const float alpha = need ? fast_exp2(m - mx2) : 1.0f;
-                    ptx::tmem_ld_wait();                       // (also retires the two S loads above)
+                    for (int i = 0; i < 8; ++i) {
+                        const float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
+                        float p0 = fast_exp2(fmaf(s0, LOG2E, -m));
+                        float p1 = fast_exp2(fmaf(s1, LOG2E, -m));
+                        if (MASKED) {
+                            if (c * 16 + 2 * i >= n_valid) p0 = 0.f; else mx = fmaxf(mx, s0);
+                            if (c * 16 + 2 * i + 1 >= n_valid) p1 = 0.f; else mx = fmaxf(mx, s1);
+                        } else {
+                            mx = fmaxf(mx, fmaxf(s0, s1));
+                        }
+                        rs += p0 + p1;
+                        __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+                        pk[i] = *reinterpret_cast<uint32_t*>(&hb);
+                    }
+                    tmem_st_32x8(p_addr + c * 8, pk);
+                };
+                ptx::tmem_ld_32x16(s_addr, va);
+                ptx::tmem_ld_wait();
+                ptx::tmem_ld_32x16(s_addr + 16, vb);
+                emit(va, 0);
+                ptx::tmem_ld_wait();
+                ptx::tmem_ld_32x16(s_addr + 32, va);
+                emit(vb, 1);
+                ptx::tmem_ld_wait();
+                ptx::tmem_ld_32x16(s_addr + 48, vb);
+                emit(va, 2);
+                ptx::tmem_ld_wait();
+                emit(vb, 3);
+                const float mx2 = fmaxf(mx, exchange(mx)) * LOG2E;    // the whole row's maximum in this tile
+                const bool need = mx2 > m + 8.0f;
+                if (!__any_sync(0xffffffffu, need)) { l += rs; break; }   // both warps of the row decide alike
+                // rare: move the reference, rescale this half of O and l, then redo the tile's probabilities
+                const float alpha = need ? fast_exp2(m - mx2) : 1.0f;
+                if (j > 0) {
                     uint32_t o[32];
+                    ptx::tmem_ld_32x32(o_addr, o);
+                    ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < DH / 32; ++c) {
-                        ptx::tmem_ld_32x32(tmem + lane_addr + TM_O + c * 32, o);
-                        ptx::tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st_32x32(tmem + lane_addr + TM_O + c * 32, o);
-                    }
-                    ptx::tmem_st_wait();
-                    l *= alpha;
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st_32x32(o_addr, o);
                 }
+                l *= alpha;
+                if (need) m = mx2;
             }
-            if (need) m = mx2;
-            // ---- pass 2: probabilities against m, row sum, bf16 P back into TMEM
-            float rs = 0.f;
-            auto emit = [&](const uint32_t* v, int c) {       // 32 scores -> 16 packed words of P
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), LOG2E, -m));
-                    float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, -m));
-                    if (MASKED) {
-                        if (c * 32 + 2 * i >= n_valid) p0 = 0.f;
-                        if (c * 32 + 2 * i + 1 >= n_valid) p1 = 0.f;
-                    }
-                    rs += p0 + p1;
-                    __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-                    pk[i] = *reinterpret_cast<uint32_t*>(&hb);
-                }
-                tmem_st_32x16(tmem + lane_addr + TM_P + c * 16, pk);
-            };
-            ptx::tmem_ld_wait();
-            emit(va, 0);
-            ptx::tmem_ld_32x32(s_addr + 64, va);
-            emit(vb, 1);
-            ptx::tmem_ld_32x32(s_addr + 96, vb);
-            ptx::tmem_ld_wait();
-            emit(va, 2);
-            emit(vb, 3);
             ptx::tmem_st_wait();
-            l += rs;
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_s_free);     // S fully consumed: next Q K^T may overwrite it
             ptx::mbar_arrive(bar_p_full);     // P written, O rescaled if needed: P V may run
@@ -278,25 +299,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const CUtensorMap* __rest
         tile(NT - 1, std::true_type{});
         ptx::mbar_wait(bar_o_full, (NT - 1) & 1);
         ptx::tc_fence_after();
-        const float inv = 1.0f / l;
-        bf16* o = out + (int64_t)(out_row + r) * d_model + h * DH;
+        const float inv = 1.0f / (l + exchange(l));
+        bf16* o = out + (int64_t)(out_row + r) * d_model + h * DH + half * (DH / 2);
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(o_addr, v);                        // warp-collective: before the row predicate
+        ptx::tmem_ld_wait();
+        if (r < n_q) {
 #pragma unroll
-        for (int c = 0; c < DH / 32; ++c) {
-            uint32_t v[32];
-            ptx::tmem_ld_32x32(tmem + lane_addr + TM_O + c * 32, v);      // warp-collective: before the row predicate
-            ptx::tmem_ld_wait();
-            if (r < n_q) {
-#pragma unroll
-                for (int e8 = 0; e8 < 4; ++e8) {
-                    uint4 u;
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[e8 * 8 + 0]) * inv, __uint_as_float(v[e8 * 8 + 1]) * inv);
-                    __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[e8 * 8 + 2]) * inv, __uint_as_float(v[e8 * 8 + 3]) * inv);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[e8 * 8 + 4]) * inv, __uint_as_float(v[e8 * 8 + 5]) * inv);
-                    __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[e8 * 8 + 6]) * inv, __uint_as_float(v[e8 * 8 + 7]) * inv);
-                    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-                    u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-                    reinterpret_cast<uint4*>(o)[c * 4 + e8] = u;
-                }
+            for (int e8 = 0; e8 < 4; ++e8) {
+                uint4 u;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[e8 * 8 + 0]) * inv, __uint_as_float(v[e8 * 8 + 1]) * inv);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[e8 * 8 + 2]) * inv, __uint_as_float(v[e8 * 8 + 3]) * inv);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[e8 * 8 + 4]) * inv, __uint_as_float(v[e8 * 8 + 5]) * inv);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[e8 * 8 + 6]) * inv, __uint_as_float(v[e8 * 8 + 7]) * inv);
+                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+                reinterpret_cast<uint4*>(o)[e8] = u;
             }
         }
     }
@@ -345,9 +363,9 @@ void dec_cross_attention_tcgen05(const void* q, int total_rows, const DecJob* jo
         set = true;
     }
     dim3 grid((max_rows + BQ - 1) / BQ, n_head, n_jobs);
-    attn_tc_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm, reinterpret_cast<const CUtensorMap*>(kv_maps_dev), jobs, layer,
-                                                             align_rank, n_head, d_model, reinterpret_cast<bf16*>(out));
-    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(launch_pdl(attn_tc_kernel<true>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM, st, tm,
+                          reinterpret_cast<const CUtensorMap*>(kv_maps_dev), jobs, layer, align_rank, n_head, d_model,
+                          reinterpret_cast<bf16*>(out)));
 }
 
 }  // namespace wlk

@@ -40,6 +40,31 @@ struct Error {
                                " in " #expr " @ " __FILE__ ":" + std::to_string(__LINE__)};    \
     } while (0)
 
+// ---------------------------------------------------------------------------------
+// Programmatic dependent launch for the decoder's chains of short kernels: the next kernel's CTAs become
+// resident (and run their prologue -- barrier init, TMEM allocation, weight-panel TMA) while the previous
+// kernel drains.  Contract: a kernel launched through launch_pdl() executes ptx::griddep_wait() before it
+// touches anything an earlier kernel produced (or still reads), so completion stays transitive along the
+// chain; WLK_PDL=0 turns the attribute off (plain stream order).
+// ---------------------------------------------------------------------------------
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 enum DType { DT_F32 = 0, DT_BF16 = 1 };
 inline size_t dtype_size(int t) { return t == DT_F32 ? 4 : 2; }
 

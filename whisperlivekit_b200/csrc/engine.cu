@@ -12,6 +12,15 @@
 
 namespace wlk {
 
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* v = getenv("WLK_PDL");
+        return !(v && v[0] == '0');
+    }();
+    return on;
+}
+
+
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 

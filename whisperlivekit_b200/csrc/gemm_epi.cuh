@@ -147,6 +147,15 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int ban
     *m_blk = b * band + (r - (*n_blk) * h);
 }
 
+// Pull the fp32 residual values this thread will add (its own row, `n_cols` columns from n_begin) into L2 while
+// the tile's MMAs are still running, so the epilogue's residual loads are L2 hits instead of HBM round trips.
+__device__ __forceinline__ void epilogue_prefetch_residual(const EpiRow& row, int n_begin, int n_cols, int N) {
+    if (row.res == nullptr) return;
+    const char* p = reinterpret_cast<const char*>(row.res + n_begin);
+    const int bytes = min(n_cols, max(0, N - n_begin)) * 4;
+    for (int off = 0; off < bytes; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+}
+
 // split-K, phase 1: dump this K range's raw accumulators of the warp's rows/columns to the global scratch
 __device__ __forceinline__ void epilogue_store_partials(float* dst_row /* scratch row of this thread */, bool row_valid,
                                                         uint32_t tmem_row_addr, int col_begin, int n_chunks) {

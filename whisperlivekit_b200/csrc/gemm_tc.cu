@@ -94,6 +94,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int kb_per_split = (num_k_total + splits - 1) / splits;
     const int band = max(1, (int)gridDim.x / 2);
 
+    ptx::griddep_launch();
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmW);
@@ -119,6 +120,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            // The weight panels never depend on the previous kernel: the first ring-full of them is requested
+            // before the grid-dependency wait, so under programmatic dependent launch the weight stream of this
+            // GEMM overlaps the tail of whatever produced its activations.  `early` counts those k-blocks.
+            int early = 0;
+            if ((int)blockIdx.x < num_tiles) {
+                const int sp = blockIdx.x / num_mn, mn = blockIdx.x - sp * num_mn;
+                int m_blk, n_blk;
+                tile_coords(mn, num_m, num_n, band, &m_blk, &n_blk);
+                const int kb0 = sp * kb_per_split;
+                early = min(STAGES, min(num_k_total, (sp + 1) * kb_per_split) - kb0);
+                for (int i = 0; i < early; ++i) {
+                    ptx::mbar_arrive_expect_tx(bar_full + 8 * i, L::A_BYTES + L::B_BYTES);
+                    ptx::tma_load_2d(sB + i * L::B_BYTES, &tmW, bar_full + 8 * i, (kb0 + i) * BK, n_blk * BN);
+                }
+            }
+            ptx::griddep_wait();
             uint32_t stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int sp = tile / num_mn, mn = tile - sp * num_mn;
@@ -126,10 +143,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tile_coords(mn, num_m, num_n, band, &m_blk, &n_blk);
                 const int kb_end = min(num_k_total, (sp + 1) * kb_per_split);
                 for (int kb = sp * kb_per_split; kb < kb_end; ++kb) {
-                    ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, L::A_BYTES + L::B_BYTES);
+                    if (early > 0) {
+                        --early;                       // slot is fresh and its W panel is already in flight
+                    } else {
+                        ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, L::A_BYTES + L::B_BYTES);
+                        ptx::tma_load_2d(sB + stage * L::B_BYTES, &tmW, bar_full + 8 * stage, kb * BK, n_blk * BN);
+                    }
                     ptx::tma_load_2d(sA + stage * L::A_BYTES, &tmA, bar_full + 8 * stage, kb * BK, m_blk * BM);
-                    ptx::tma_load_2d(sB + stage * L::B_BYTES, &tmW, bar_full + 8 * stage, kb * BK, n_blk * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -172,12 +193,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* sbias = reinterpret_cast<float*>(smem_gen + L::STG_OFF) + ew * EPI_BIAS_FLOATS;
         volatile int* sk_flag = reinterpret_cast<volatile int*>(smem_gen + (tmem_slot - smem_base) + 8);
         uint32_t it = 0;
+        ptx::griddep_wait();                          // residual, split-K scratch and C belong to the stream's past
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int sp = tile / num_mn, mn = tile - sp * num_mn;
             int m_blk, n_blk;
             tile_coords(mn, num_m, num_n, band, &m_blk, &n_blk);
             const uint32_t as = it & 1, ap = (it >> 1) & 1;
             const EpiRow row = epi_row(epi, m_blk * BM + q * 32 + lane, M);
+            epilogue_prefetch_residual(row, n_blk * BN + hc * (BN / 2), BN / 2, N);
             ptx::mbar_wait(bar_tfull + 8 * as, ap);
             ptx::tc_fence_after();
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
@@ -249,8 +272,8 @@ void launch(const GemmArgs& g, cudaStream_t st, int num_sms, int splits = 1) {
     }
     const int num_tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * splits;
     const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-    gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, L::DYN, st>>>(tmA, tmW, g.M, g.N, g.K, splits, g_sk_scratch, g_sk_counters, g.epi);
-    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(launch_pdl(gemm_tc_kernel<BN, STAGES>, dim3(grid), dim3(NUM_THREADS), L::DYN, st, tmA, tmW, g.M, g.N, g.K, splits,
+                          g_sk_scratch, g_sk_counters, g.epi));
 }
 
 }  // namespace

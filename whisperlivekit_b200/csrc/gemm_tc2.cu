@@ -105,7 +105,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int num_m = (M + BM2 - 1) / BM2, num_n = (N + BN2 - 1) / BN2;
     const int num_tiles = num_m * num_n;
     const int num_k = (K + BK2 - 1) / BK2;
-    const int band = max(1, num_clusters / 2);        // two n-blocks of a band in flight at a time
+    // two n-blocks of a band in flight at a time; the band's A rows (256 x K bf16 each) should stay L2-resident
+    const int band = max(1, min(num_clusters / 2, (int)((48u << 20) / (512u * (uint32_t)K))));
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
@@ -186,6 +187,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tile_coords(tile, num_m, num_n, band, &m_blk, &n_blk);
             const uint32_t as = it & 1, ap = (it >> 1) & 1;
             const EpiRow row = epi_row(epi, m_blk * BM2 + rank * 128 + q * 32 + lane, M);
+            epilogue_prefetch_residual(row, n_blk * BN2 + hc * COLS_PER_WARP, COLS_PER_WARP, N);
             ptx::mbar_wait(bar_tfull + 8 * as, ap);
             ptx::tc_fence_after();
             epilogue_warp_tile(epi, sbias, row, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN2,

@@ -1,6 +1,7 @@
 // Non-GEMM kernels of the streaming-Whisper hot path (sm_100a).  Everything here is
 // bandwidth- or latency-bound SIMT code; the tensor-core kernels live in gemm_tc.cu / attn_tc.cu.
 #include "kernels.cuh"
+#include "ptx.cuh"
 
 namespace wlk {
 
@@ -275,6 +276,8 @@ template <typename TO>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ b,
                  TO* __restrict__ out, int64_t ldo, int rows, int d, const int32_t* __restrict__ row_index) {
+    ptx::griddep_launch();                   // programmatic dependent launch: see launch_pdl (common.cuh)
+    ptx::griddep_wait();
     constexpr int MAXV = 10;                          // float4 per lane: d <= 1280
     const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -316,14 +319,15 @@ void layernorm(const float* x, int64_t ldx, const float* w, const float* b, void
     if (rows <= 0) return;
     WLK_CHECK(d % 4 == 0 && d <= 1280 && ldx % 4 == 0 && ldo % 4 == 0, "layernorm: d=%d must be a multiple of 4 and <= 1280", d);
     int grid = (rows + 7) / 8;
-    if (out_type == DT_F32) layernorm_kernel<float><<<grid, 256, 0, st>>>(x, ldx, w, b, (float*)out, ldo, rows, d, row_index);
-    else layernorm_kernel<bf16><<<grid, 256, 0, st>>>(x, ldx, w, b, (bf16*)out, ldo, rows, d, row_index);
-    CUDA_CHECK(cudaGetLastError());
+    if (out_type == DT_F32) CUDA_CHECK(launch_pdl(layernorm_kernel<float>, dim3(grid), dim3(256), 0, st, x, ldx, w, b, (float*)out, ldo, rows, d, row_index));
+    else CUDA_CHECK(launch_pdl(layernorm_kernel<bf16>, dim3(grid), dim3(256), 0, st, x, ldx, w, b, (bf16*)out, ldo, rows, d, row_index));
 }
 
 __global__ void embed_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ pos,
                              const float* __restrict__ emb, const float* __restrict__ pos_emb, float* __restrict__ x,
                              int rows, int d) {
+    ptx::griddep_launch();                   // programmatic dependent launch: see launch_pdl (common.cuh)
+    ptx::griddep_wait();
     int r = blockIdx.x;
     if (r >= rows) return;
     const float* e = emb + (int64_t)tok[r] * d;
@@ -333,8 +337,7 @@ __global__ void embed_kernel(const int32_t* __restrict__ tok, const int32_t* __r
 void embed_tokens(const int32_t* tokens_dev, const int32_t* pos_dev, const float* emb, const float* pos_emb, float* x,
                   int rows, int d, cudaStream_t st) {
     if (rows <= 0) return;
-    embed_kernel<<<rows, 256, 0, st>>>(tokens_dev, pos_dev, emb, pos_emb, x, rows, d);
-    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(launch_pdl(embed_kernel, dim3(rows), dim3(256), 0, st, tokens_dev, pos_dev, emb, pos_emb, x, rows, d));
 }
 
 // =====================================================================================
@@ -495,6 +498,8 @@ template <typename T, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 dec_self_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, int layer, int n_head, int d_model,
                      int n_text_ctx, T* __restrict__ out) {
+    ptx::griddep_launch();                   // programmatic dependent launch: see launch_pdl (common.cuh)
+    ptx::griddep_wait();
     constexpr int MAXK = 14;                 // ceil(448 / 32) keys per lane
     constexpr int VN = RowVec<T>::N;
     __shared__ float qs[WARPS][64];
@@ -571,13 +576,12 @@ void dec_self_attention(const void* q, int type, const DecJob* jobs, int n_jobs,
     WLK_CHECK(n_text_ctx <= 448, "dec_self_attention: n_text_ctx %d > 448", n_text_ctx);
     dim3 grid(n_head, n_jobs);
     if (max_rows <= 1) {                      // token step: one warp per (session, head), a single wave of tiny CTAs
-        if (type == DT_F32) dec_self_attn_kernel<float, 1><<<grid, 32, 0, st>>>((const float*)q, jobs, layer, n_head, d_model, n_text_ctx, (float*)out);
-        else dec_self_attn_kernel<bf16, 1><<<grid, 32, 0, st>>>((const bf16*)q, jobs, layer, n_head, d_model, n_text_ctx, (bf16*)out);
+        if (type == DT_F32) CUDA_CHECK(launch_pdl(dec_self_attn_kernel<float, 1>, grid, dim3(32), 0, st, (const float*)q, jobs, layer, n_head, d_model, n_text_ctx, (float*)out));
+        else CUDA_CHECK(launch_pdl(dec_self_attn_kernel<bf16, 1>, grid, dim3(32), 0, st, (const bf16*)q, jobs, layer, n_head, d_model, n_text_ctx, (bf16*)out));
     } else {
-        if (type == DT_F32) dec_self_attn_kernel<float, 8><<<grid, 256, 0, st>>>((const float*)q, jobs, layer, n_head, d_model, n_text_ctx, (float*)out);
-        else dec_self_attn_kernel<bf16, 8><<<grid, 256, 0, st>>>((const bf16*)q, jobs, layer, n_head, d_model, n_text_ctx, (bf16*)out);
+        if (type == DT_F32) CUDA_CHECK(launch_pdl(dec_self_attn_kernel<float, 8>, grid, dim3(256), 0, st, (const float*)q, jobs, layer, n_head, d_model, n_text_ctx, (float*)out));
+        else CUDA_CHECK(launch_pdl(dec_self_attn_kernel<bf16, 8>, grid, dim3(256), 0, st, (const bf16*)q, jobs, layer, n_head, d_model, n_text_ctx, (bf16*)out));
     }
-    CUDA_CHECK(cudaGetLastError());
 }
 
 // =====================================================================================
@@ -595,6 +599,8 @@ template <typename T, int QB>
 __global__ void __launch_bounds__(256)
 dec_cross_attn_kernel(const T* __restrict__ q, const DecJob* __restrict__ jobs, int layer, int n_head, int d_model,
                       int n_text_ctx, const int32_t* __restrict__ align_rank, T* __restrict__ out, int only_align) {
+    ptx::griddep_launch();                   // programmatic dependent launch: see launch_pdl (common.cuh)
+    ptx::griddep_wait();
     constexpr int VN = RowVec<T>::N;          // elements per lane
     constexpr int LPK = 64 / VN;              // lanes per key row  (8 bf16 / 16 fp32)
     constexpr int KPW = 32 / LPK;             // key rows per warp instruction (4 / 2)
@@ -741,8 +747,7 @@ static void launch_cross(const void* q, const DecJob* jobs, int n_jobs, int laye
         CUDA_CHECK(cudaFuncSetAttribute(dec_cross_attn_kernel<T, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         set = true;
     }
-    dec_cross_attn_kernel<T, QB><<<grid, 256, smem, st>>>((const T*)q, jobs, layer, n_head, d_model, n_text_ctx, align_rank, (T*)out, only_align);
-    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(launch_pdl(dec_cross_attn_kernel<T, QB>, grid, dim3(256), (size_t)smem, st, (const T*)q, jobs, layer, n_head, d_model, n_text_ctx, align_rank, (T*)out, only_align));
 }
 void dec_cross_attention(const void* q, int type, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model,
                          int n_text_ctx, const int32_t* align_rank, void* out, int max_rows, bool only_align_heads,

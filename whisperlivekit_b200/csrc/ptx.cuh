@@ -64,6 +64,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// ---- programmatic dependent launch (see launch_pdl in common.cuh) ----------------------
+// wait: blocks until every grid this one depends on has completed and its writes are visible (no-op when the
+// launch carried no PDL attribute).  launch_dependents: lets the next kernel in the stream start scheduling
+// once every CTA of this grid has issued it (or exited).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- TMA ------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
