@@ -292,7 +292,7 @@ def main():
                      ms_per_step=ms_e2e / args.steps),
             gpu_launches=launches,
             clocks=clocks,
-            roofline=dict(bound="tensor", kernel="gemm_tc_kernel (encoder GEMMs, class gemm_enc)", achieved=ach,
+            roofline=dict(bound="tensor", kernel="gemm_tc2_kernel (cta_group::2 pair GEMM; encoder GEMMs, class gemm_enc)", achieved=ach,
                           peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=ach / peaks["bf16_tflops"], traffic=None,
                           peak_source=peaks["source"],
                           flops_per_launch=g["flops"] / max(1, g["launches"]), ms_per_launch=g["ms"] / max(1, g["launches"])),

@@ -385,6 +385,15 @@ class OracleEngine:
         return res
 
     # -- debug taps ---------------------------------------------------------
+    # word-timestamp math of the LocalAgreement path (same host-array entry points as WhisperEngine)
+    def median_filter_host(self, x, width: int = 7):
+        from oracle import timing_oracle
+        return timing_oracle.median_filter(np.ascontiguousarray(x, np.float32), width)
+
+    def dtw_host(self, x):
+        from oracle import timing_oracle
+        return timing_oracle.dtw(np.ascontiguousarray(x, np.float32))
+
     def read_mel(self, sid):        return self._s[sid]["mel"][0].numpy()
     def read_encoder(self, sid):    return self._s[sid]["xa"][0].numpy()
     def read_logits(self, sid):     return self._s[sid]["logits"].numpy()

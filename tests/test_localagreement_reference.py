@@ -57,3 +57,10 @@ def test_transcribe_over_b200_model_equals_reference(name):
     np.testing.assert_allclose(gp, rp, rtol=1e-4, atol=1e-6)
     assert len(asr.ts_words(got)) == len(rw)
     assert asr.segments_end_ts(got) == [s["end"] for s in ref["segments"]]
+    # the word-timestamp pass reused the segment's encoder output instead of encoding the same mel twice,
+    # and median filter / DTW went through the engine's entry points (install_native_timing)
+    assert asr.model.encoder_reuses == asr.model.encoder_calls >= 1
+    import whisperlivekit.whisper.timing as timing
+    assert hasattr(timing, "_b200_saved")
+    from whisperlivekit_b200.localagreement import uninstall_native_timing
+    uninstall_native_timing()

@@ -42,6 +42,10 @@ def test_cuda_median_and_dtw_match_reference():
         torch.cuda.synchronize()
         t, f = eng.op_dtw(neg.data_ptr(), x.shape[0], x.shape[1])
         assert np.array_equal(t, ti) and np.array_equal(f, fi)
+        # host-array entry points used by the LocalAgreement shim (localagreement.install_native_timing)
+        assert np.array_equal(eng.median_filter_host(x, 7), med)
+        t, f = eng.dtw_host(-med)
+        assert np.array_equal(t, ti) and np.array_equal(f, fi)
     xq = torch.from_numpy(G["xq"]).cuda()
     torch.cuda.synchronize()
     t, f = eng.op_dtw(xq.data_ptr(), *G["xq"].shape)

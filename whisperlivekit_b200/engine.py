@@ -250,6 +250,27 @@ class WhisperEngine:
         L.check(self.lib.wlk_op_dtw(self.h, x_ptr, n_tokens, n_frames, _ptr(ti), _ptr(fi), C.byref(n)))
         return ti[: n.value].copy(), fi[: n.value].copy()
 
+    def median_filter_host(self, x: np.ndarray, width: int = 7) -> np.ndarray:
+        """whisper.timing.median_filter on a host array [..., cols] (reflect pad, odd width): H2D, wlk_op_median_filter,
+        D2H.  Staging goes through torch's allocator (plumbing); the arithmetic is the native kernel."""
+        import torch
+        x = np.ascontiguousarray(x, np.float32)
+        cols = x.shape[-1]
+        xd = torch.from_numpy(x.reshape(-1, cols)).to(f"cuda:{self.device}")
+        od = torch.empty_like(xd)
+        torch.cuda.synchronize()
+        self.op_median_filter(xd.data_ptr(), od.data_ptr(), xd.shape[0], cols, width)
+        self.sync()
+        return od.cpu().numpy().reshape(x.shape)
+
+    def dtw_host(self, x: np.ndarray):
+        """whisper.timing.dtw on a host cost matrix [n_tokens, n_frames] -> (text_indices, time_indices)."""
+        import torch
+        x = np.ascontiguousarray(x, np.float32)
+        xd = torch.from_numpy(x).to(f"cuda:{self.device}")
+        torch.cuda.synchronize()
+        return self.op_dtw(xd.data_ptr(), x.shape[0], x.shape[1])
+
     # -- lifetime ------------------------------------------------------------------------
     def close(self) -> None:
         if not self._closed:

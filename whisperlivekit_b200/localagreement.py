@@ -114,6 +114,9 @@ class B200TranscribeModel:
             mask[l, h] = True
         self.alignment_heads = mask.to_sparse()
         self.sid = engine.open_session()
+        self._last_mel = None
+        self.encoder_calls = 0
+        self.encoder_reuses = 0
         self._decode_fn, self._detect_fn, self._transcribe_fn = decode_function, detect_language_function, transcribe_function
 
     # -- attributes the reference reads ---------------------------------------------------
@@ -142,7 +145,15 @@ class B200TranscribeModel:
             if m.shape[0] != 1:
                 raise NotImplementedError("B200 LocalAgreement model: one audio segment per call")
             m = m[0]
-        self.engine.encode_mel(self.sid, m, 1500)
+        # The word-timestamp pass (timing.py:197) asks for model(mel, tokens) on the very segment that
+        # DecodingTask just encoded: the session still holds that encoder output and its cross-K/V, so a
+        # bit-identical mel is not encoded twice (halves the encoder work of this path).
+        if self._last_mel is not None and self._last_mel.shape == m.shape and np.array_equal(self._last_mel, m):
+            self.encoder_reuses += 1
+        else:
+            self.engine.encode_mel(self.sid, m, 1500)
+            self._last_mel = m.copy()
+            self.encoder_calls += 1
         return AudioFeatures(self, self.sid)
 
     embed_audio = encoder
@@ -197,13 +208,46 @@ class B200TranscribeModel:
         self.engine.close_session(self.sid)
 
 
+def install_native_timing(engine):
+    """Route the reference's word-timestamp kernels to the engine: ``whisper.timing.median_filter`` and
+    ``whisper.timing.dtw`` (timing.py:19-54,141-151; their GPU versions are the Triton kernels of
+    whisper/triton_ops.py) are looked up in the module at call time by ``find_alignment`` (timing.py:204-213),
+    so rebinding the two names is the whole integration.  Both native kernels are bit-exact against the
+    reference's CPU path (tests/test_timing.py), hence word boundaries do not move."""
+    import torch
+    import whisperlivekit.whisper.timing as timing
+
+    def median_filter(x, filter_width: int):
+        pad = filter_width // 2
+        if x.shape[-1] <= pad:                      # same early-out as the reference (timing.py:23-26)
+            return x
+        return torch.from_numpy(engine.median_filter_host(x.detach().cpu().float().numpy(), filter_width))
+
+    def dtw(x):
+        text_indices, time_indices = engine.dtw_host(x.detach().cpu().float().numpy())
+        return np.stack([text_indices, time_indices]).astype(np.int64)
+
+    if not hasattr(timing, "_b200_saved"):
+        timing._b200_saved = (timing.median_filter, timing.dtw)
+    timing.median_filter, timing.dtw = median_filter, dtw
+
+
+def uninstall_native_timing():
+    import whisperlivekit.whisper.timing as timing
+    if hasattr(timing, "_b200_saved"):
+        timing.median_filter, timing.dtw = timing._b200_saved
+        del timing._b200_saved
+
+
 class B200WhisperASR:
     """Mirror of the reference's ``WhisperASR`` (local_agreement/backends.py:39-99) over B200TranscribeModel:
     same ``transcribe / ts_words / segments_end_ts / use_vad`` duck-type that ``OnlineASRProcessor`` drives."""
     sep = " "
 
-    def __init__(self, engine, lan: str = "en"):
+    def __init__(self, engine, lan: str = "en", native_timing: bool = True):
         self.model = B200TranscribeModel(engine)
+        if native_timing:
+            install_native_timing(engine)
         self.original_language = None if lan == "auto" else lan
         self.transcribe_kargs = {}
 
