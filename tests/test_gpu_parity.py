@@ -219,3 +219,49 @@ def test_localagreement_entry_points_match_oracle():
     eng.append_audio(s2, audio); eng.encode([s2])
     assert np.abs(eng.read_encoder(s2) - outs[0][0]).max() < 1e-3
     eng.close_session(se); eng.close_session(s2)
+
+
+def test_batching_shim_threads_equal_sequential_sessions():
+    """Six sessions driven from six threads through batching.BatchingEngine (coalesced into batched C-ABI
+    calls) emit exactly the tokens / attended frames of the same sessions driven one after the other."""
+    import threading
+    from whisperlivekit_b200.alignatt import AlignAttConfig, StreamingAlignAtt
+    from whisperlivekit_b200.batching import BatchingEngine
+    from whisperlivekit_b200.engine import WhisperEngine
+    g, dims, sd, audio, heads = case_setup("micro")
+    for k in list(_ENGINES):
+        _ENGINES.pop(k).close()
+    eng = WhisperEngine(dims, sd, heads, precision="fp32", max_sessions=8, max_batch=8)
+    n = 6
+
+    def drive(engine, threaded):
+        pols = [StreamingAlignAtt(engine, AlignAttConfig(nonspeech_prob=1.01)) for _ in range(n)]
+        out = [[] for _ in pols]
+
+        def run(i):
+            a = np.concatenate([audio[3000 * i:], synthetic_audio(2.0, seed=50 + i)])
+            for c in range(4):
+                pols[i].insert_audio(a[c * 8000:(c + 1) * 8000])
+                tr = pols[i].infer()
+                out[i].append((tr.stop, tuple(tr.step_tokens), tuple(tr.step_frames)))
+
+        if threaded:
+            ths = [threading.Thread(target=run, args=(i,)) for i in range(n)]
+            [t.start() for t in ths]
+            [t.join(timeout=120) for t in ths]
+            assert not any(t.is_alive() for t in ths)
+        else:
+            for i in range(n):
+                run(i)
+        for p in pols:
+            p.close()
+        return out
+
+    direct = drive(eng, False)
+    be = BatchingEngine(eng, max_batch=8, max_wait_s=0.01)
+    got = drive(be, True)
+    be.close()
+    assert got == direct
+    assert sum(len(x[1]) for o in got for x in o) > 20            # the policy did decode
+    assert be.stats["max_sessions_in_call"] >= 2
+    eng.close()

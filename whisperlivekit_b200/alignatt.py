@@ -175,6 +175,16 @@ class StreamingAlignAtt:
 
     # -- the template infer() ------------------------------------------------
     def infer(self, is_last: bool = False) -> InferTrace:
+        begin = getattr(self.engine, "begin_iter", None)
+        if begin is None:
+            return self._infer(is_last)
+        begin()                                   # BatchingEngine: one more session inside a policy iteration
+        try:
+            return self._infer(is_last)
+        finally:
+            self.engine.end_iter()
+
+    def _infer(self, is_last: bool = False) -> InferTrace:
         """reference align_att_base.py:174-322 (control flow), one engine call per hook."""
         eng, sid, cfg = self.engine, self.sid, self.cfg
         tr = InferTrace()
@@ -331,6 +341,18 @@ class AlignAttHooks:
             self.engine.close_session(self.sid)
         except Exception:
             pass
+
+    def infer(self, is_last: bool = False):
+        """The reference's template (align_att_base.py:174-322), bracketed so that a BatchingEngine knows how
+        many sessions are inside a policy iteration and can fire a batch as soon as all of them have called."""
+        begin = getattr(self.engine, "begin_iter", None)
+        if begin is None:
+            return super().infer(is_last=is_last)
+        begin()
+        try:
+            return super().infer(is_last=is_last)
+        finally:
+            self.engine.end_iter()
 
     # ---- state -----------------------------------------------------------------
     def _init_state(self, cfg):

@@ -1,0 +1,207 @@
+"""Batching-aware caller shim.
+
+WhisperLiveKit drives every session from its own worker thread (reference audio_processor.py:543-551:
+``await asyncio.to_thread(self.transcription.process_iter)``) and each thread issues single-session model
+calls (``_encode``, ``_get_logits_and_cross_attn``, ... -- simul_whisper/align_att_base.py:174-322).  On the
+B200 engine the unit of efficiency is a *batched* call: one ``wlk_encode`` over 96 sessions costs about as
+much GPU time as 96 back-to-back single-session calls cost in launch latency alone.
+
+``BatchingEngine`` keeps the per-session call surface (it duck-types ``WhisperEngine``) and coalesces
+concurrent calls of the same kind into one C-ABI call:
+
+    caller threads                      dispatcher thread
+    --------------                      -----------------
+    eng.encode([sid])   --submit-->     gather requests with the same (op, static args)
+    (blocks on a Future)                until every in-flight caller has submitted, or `max_wait_s` passed
+                         <--result--    engine.encode([sid_a, sid_b, ...]) ; split the results
+
+Semantics are unchanged: one call in flight per session (as the reference guarantees), results are what the
+single-session call would have returned (the batched kernels are batch-invariant: tests/test_gpu_parity.py
+``test_batched_equals_single``), errors are delivered to exactly the callers of the failing batch.
+``submit()`` returns a ``concurrent.futures.Future`` so an asyncio caller can ``await asyncio.wrap_future(f)``
+instead of parking an OS thread per stream.
+"""
+from __future__ import annotations
+
+import threading
+import time
+from collections import OrderedDict
+from concurrent.futures import Future
+from typing import Any, Dict, List, Sequence, Tuple
+
+# op name -> how to merge single-session requests into one engine call and split the result
+_BATCHED = ("encode", "decode", "no_speech_prob", "suppress", "greedy_and_align")
+
+
+class _Request:
+    __slots__ = ("op", "key", "sids", "payload", "future", "t_submit")
+
+    def __init__(self, op, key, sids, payload):
+        self.op, self.key, self.sids, self.payload = op, key, list(sids), payload
+        self.future: Future = Future()
+        self.t_submit = time.perf_counter()
+
+
+class BatchingEngine:
+    """Duck-types ``WhisperEngine``; see the module docstring.
+
+    max_batch    upper bound on sessions per engine call (the engine's own ``max_batch``)
+    max_wait_s   how long the dispatcher holds the first request of a batch for companions
+    """
+
+    def __init__(self, engine, max_batch: int = 64, max_wait_s: float = 0.002):
+        self.engine = engine
+        self.max_batch = int(max_batch)
+        self.max_wait_s = float(max_wait_s)
+        self._lock = threading.RLock()              # serialises every call into the wrapped engine
+        self._cv = threading.Condition()
+        self._pending: List[_Request] = []
+        self._inflight = 0                          # callers inside begin_iter()/end_iter()
+        self._stop = False
+        self.stats: Dict[str, Any] = dict(calls=0, requests=0, sessions=0, max_sessions_in_call=0,
+                                          by_op={op: dict(calls=0, sessions=0) for op in _BATCHED})
+        self._thread = threading.Thread(target=self._run, name="wlk-b200-batcher", daemon=True)
+        self._thread.start()
+
+    # -- static attributes of the wrapped engine -------------------------------------------------------
+    def __getattr__(self, name):
+        # anything not batched (attributes such as dims/specials/align_heads, and debug taps) goes straight through
+        attr = getattr(self.engine, name)
+        if callable(attr):
+            def locked(*a, **k):
+                with self._lock:
+                    return attr(*a, **k)
+            return locked
+        return attr
+
+    # -- bracket a caller's policy iteration: lets the dispatcher fire as soon as everybody has arrived --
+    def begin_iter(self) -> None:
+        with self._cv:
+            self._inflight += 1
+
+    def end_iter(self) -> None:
+        with self._cv:
+            self._inflight = max(0, self._inflight - 1)
+            self._cv.notify_all()
+
+    # -- submission ---------------------------------------------------------------------------------------
+    def submit(self, op: str, sids: Sequence[int], *payload, **static) -> Future:
+        """Queue one request; the Future resolves to what ``engine.<op>(sids, ...)`` returns."""
+        if op not in _BATCHED:
+            raise ValueError(f"{op} is not a batched operation")
+        key = (op,) + tuple(sorted((k, _freeze(v)) for k, v in static.items()))
+        if op == "suppress":
+            key += (_freeze(payload[0]),)
+        req = _Request(op, key, sids, (payload, static))
+        with self._cv:
+            if self._stop:
+                raise RuntimeError("BatchingEngine is closed")
+            self._pending.append(req)
+            self._cv.notify_all()
+        return req.future
+
+    def encode(self, sids):
+        return self.submit("encode", sids).result()
+
+    def decode(self, sids, tokens, sot_index: int = 0):
+        return self.submit("decode", sids, [list(t) for t in tokens], sot_index=int(sot_index)).result()
+
+    def no_speech_prob(self, sids):
+        return self.submit("no_speech_prob", sids).result()
+
+    def suppress(self, sids, token_ids):
+        return self.submit("suppress", sids, tuple(int(t) for t in token_ids)).result()
+
+    def greedy_and_align(self, sids, window_iters: int = 16):
+        return self.submit("greedy_and_align", sids, window_iters=int(window_iters)).result()
+
+    # -- dispatcher -----------------------------------------------------------------------------------------
+    def _take_batch(self) -> List[_Request]:
+        """Called with the condition held and at least one request pending: wait for companions of the oldest
+        request, then remove and return every pending request with its key (up to max_batch sessions)."""
+        first = self._pending[0]
+        deadline = first.t_submit + self.max_wait_s
+        while not self._stop:
+            same = [r for r in self._pending if r.key == first.key]
+            n_sess = sum(len(r.sids) for r in same)
+            waiting = len(self._pending)
+            everyone_here = self._inflight > 0 and waiting >= self._inflight
+            if n_sess >= self.max_batch or everyone_here:
+                break
+            left = deadline - time.perf_counter()
+            if left <= 0:
+                break
+            self._cv.wait(left)
+        batch, n = [], 0
+        for r in list(self._pending):
+            if r.key != first.key:
+                continue
+            if batch and n + len(r.sids) > self.max_batch:
+                break
+            batch.append(r)
+            n += len(r.sids)
+            self._pending.remove(r)
+        return batch
+
+    def _run(self) -> None:
+        while True:
+            with self._cv:
+                while not self._pending and not self._stop:
+                    self._cv.wait()
+                if self._stop and not self._pending:
+                    return
+                batch = self._take_batch()
+            if batch:
+                self._execute(batch)
+
+    def _execute(self, batch: List[_Request]) -> None:
+        op = batch[0].op
+        sids = [s for r in batch for s in r.sids]
+        payload, static = batch[0].payload
+        try:
+            with self._lock:
+                if op == "encode":
+                    out = self.engine.encode(sids)
+                elif op == "decode":
+                    toks = [t for r in batch for t in r.payload[0][0]]
+                    out = self.engine.decode(sids, toks, **static)
+                elif op == "no_speech_prob":
+                    out = self.engine.no_speech_prob(sids)
+                elif op == "suppress":
+                    out = self.engine.suppress(sids, list(payload[0]))
+                else:
+                    out = self.engine.greedy_and_align(sids, **static)
+        except BaseException as e:                      # delivered to the callers of this batch only
+            for r in batch:
+                r.future.set_exception(e)
+            return
+        st = self.stats
+        st["calls"] += 1
+        st["requests"] += len(batch)
+        st["sessions"] += len(sids)
+        st["max_sessions_in_call"] = max(st["max_sessions_in_call"], len(sids))
+        st["by_op"][op]["calls"] += 1
+        st["by_op"][op]["sessions"] += len(sids)
+        pos = 0
+        for r in batch:
+            n = len(r.sids)
+            r.future.set_result(None if out is None else list(out[pos: pos + n]))
+            pos += n
+
+    # -- lifetime ---------------------------------------------------------------------------------------------
+    def close(self, close_engine: bool = False) -> None:
+        with self._cv:
+            self._stop = True
+            self._cv.notify_all()
+        self._thread.join(timeout=5)
+        for r in self._pending:
+            r.future.set_exception(RuntimeError("BatchingEngine closed"))
+        self._pending.clear()
+        if close_engine:
+            self.engine.close()
+
+
+def _freeze(v):
+    if isinstance(v, (list, tuple)):
+        return tuple(_freeze(x) for x in v)
+    return v

@@ -61,9 +61,11 @@ def make_b200_alignatt_class():
     return B200AlignAtt
 
 
-def install(precision: str = "bf16", device: int = 0, max_sessions: int = 64, max_batch: int = 64):
+def install(precision: str = "bf16", device: int = 0, max_sessions: int = 64, max_batch: int = 64,
+            batching: bool = True, max_wait_s: float = 0.002):
     """Route WhisperLiveKit's SimulStreaming backend through the B200 engine (call once, before
-    TranscriptionEngine is constructed)."""
+    TranscriptionEngine is constructed).  With ``batching`` the per-session calls of the worker threads
+    (audio_processor.py:543-551) are coalesced into batched C-ABI calls by batching.BatchingEngine."""
     import whisperlivekit.simul_whisper.backend as be
     cls = make_b200_alignatt_class()
     be.AlignAtt = cls
@@ -73,6 +75,9 @@ def install(precision: str = "bf16", device: int = 0, max_sessions: int = 64, ma
         torch_model = orig_load(self, *a, **k)
         eng = engine_from_torch_whisper(torch_model, precision=precision, device=device,
                                         max_sessions=max_sessions, max_batch=max_batch)
+        if batching:
+            from .batching import BatchingEngine
+            eng = BatchingEngine(eng, max_batch=max_batch, max_wait_s=max_wait_s)
         return B200WhisperModel(eng)
 
     be.SimulStreamingASR.load_model = load_model
