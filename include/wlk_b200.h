@@ -79,6 +79,18 @@ int wlk_session_audio_len(wlk_engine* e, int32_t sid, int64_t* n);
 /* DecoderState.clean_cache (reference decoder_state.py:51-59): forget the self-KV and the
  * alignment rows of the current epoch but keep the encoder output / cross-K/V.           */
 int wlk_session_reset_decoder(wlk_engine* e, int32_t sid);
+/* Beam search (reference simul_whisper/beam.py:8-32, whisper/decoding.py:289-376; AlignAtt with
+ * decoder_type "beam", simul_whisper.py:182-192,240-243).  The reference runs the decoder on
+ * beam_size rows that share one encoder output; here a beam is a session forked from the stream's
+ * session: it has its own self-K/V, logits and alignment rows but reads the parent's encoder
+ * output and cross-K/V (no copy, 245.8 MB per session at large-v3 stay shared).  A fork holds no
+ * audio; it must be closed before its parent; encoding the parent starts a new epoch for its forks. */
+int wlk_session_fork(wlk_engine* e, int32_t parent, int32_t* child_sid);
+/* BeamPyTorchInference.rearrange_kv_cache (beam.py:15-19): for every i the self-K/V (and its
+ * length) of sessions[i] becomes that of sessions[source_indices[i]] as it was before the call.
+ * The alignment rows are NOT moved: the reference keeps its accumulated cross-attention per beam
+ * row, not per hypothesis (align_att_base.py:222-224 appends whole [beam, ...] tensors).          */
+int wlk_sessions_gather_decoder(wlk_engine* e, const int32_t* sessions, const int32_t* source_indices, int n);
 
 /* ---- hot path, batched over sessions -------------------------------------------------
  * wlk_encode: AlignAtt._encode (simul_whisper.py:299-352) = log_mel_spectrogram

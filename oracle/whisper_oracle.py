@@ -287,6 +287,26 @@ class OracleEngine:
     def close_session(self, sid: int) -> None:
         self._s.pop(sid)
 
+    def fork_session(self, parent: int) -> int:
+        """A beam row: the reference feeds one encoder output to beam_size decoder rows
+        (simul_whisper.py:240-243 repeat_interleave of the tokens, xa broadcast in model.py:148-173)."""
+        sid = self.open_session()
+        self._s[sid]["parent"] = parent
+        return sid
+
+    def _enc(self, sid: int) -> dict:
+        s = self._s[sid]
+        return self._s[s["parent"]] if "parent" in s else s
+
+    def gather_decoder(self, sids: Sequence[int], source_indices: Sequence[int]) -> None:
+        """reference simul_whisper/beam.py:15-19: self-attention K/V rows re-indexed, nothing else."""
+        snap = [{k: v for k, v in self._s[sid]["kv"].items() if ".cross_attn_" not in k} for sid in sids]
+        for i, sid in enumerate(sids):
+            kv = self._s[sid]["kv"]
+            for k in [k for k in kv if ".cross_attn_" not in k]:
+                del kv[k]
+            kv.update({k: v.clone() for k, v in snap[source_indices[i]].items()})
+
     def append_audio(self, sid: int, pcm) -> None:
         s = self._s[sid]
         s["audio"] = np.concatenate([s["audio"], np.asarray(pcm, np.float32).reshape(-1)])
@@ -316,6 +336,9 @@ class OracleEngine:
             s["mel"], s["content"] = mel, content
             s["xa"] = encoder_forward(self.W, self.dims, mel)
             s["kv"], s["iters"], s["logits"], s["sot_row"] = {}, [], None, None   # new infer epoch
+            for f in self._s.values():
+                if f.get("parent") == sid:
+                    f["kv"], f["iters"], f["logits"], f["sot_row"] = {}, [], None, None
             out.append(content)
         return out
 
@@ -324,7 +347,7 @@ class OracleEngine:
         for sid, toks in zip(sids, tokens):
             s = self._s[sid]
             t = torch.tensor([list(toks)], dtype=torch.long)
-            logits, cross = decoder_forward(self.W, self.dims, t, s["xa"], s["kv"])
+            logits, cross = decoder_forward(self.W, self.dims, t, self._enc(sid)["xa"], s["kv"])
             if not s["iters"]:
                 s["sot_row"] = logits[0, sot_index].clone()
             s["logits"] = logits[0, -1].clone()
@@ -378,7 +401,7 @@ class OracleEngine:
             s = self._s[sid]
             tok, lp = greedy_update(s["logits"])
             attn = process_cross_attention(s["iters"][-window_iters:], self.align_heads,
-                                           self.dims.n_text_layer, s["content"])
+                                           self.dims.n_text_layer, self._enc(sid)["content"])
             frame = int(torch.argmax(attn[0, -1, :]))
             s["attn"] = attn
             res.append((tok, lp, frame))

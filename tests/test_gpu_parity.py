@@ -265,3 +265,52 @@ def test_batching_shim_threads_equal_sequential_sessions():
     assert sum(len(x[1]) for o in got for x in o) > 20            # the policy did decode
     assert be.stats["max_sessions_in_call"] >= 2
     eng.close()
+
+
+def test_beam_fork_and_gather_match_oracle():
+    """Beam rows as forked sessions (wlk_session_fork: shared encoder output / cross-K/V) and
+    BeamPyTorchInference.rearrange_kv_cache as wlk_sessions_gather_decoder, against the oracle doing the same
+    operations (reference beam.py:15-19, simul_whisper.py:240-243).  fp32 mode: logits within 1e-3, frames equal."""
+    from oracle import whisper_oracle as wo
+    from whisperlivekit_b200._lib import WlkError
+    from whisperlivekit_b200.engine import WhisperEngine
+    g, dims, sd, audio, heads = case_setup("micro")
+    for k in list(_ENGINES):
+        _ENGINES.pop(k).close()
+    eng = WhisperEngine(dims, sd, heads, precision="fp32", max_sessions=4, max_batch=4)
+    orc = wo.OracleEngine(dims, sd, heads)
+    prefix = list(g["forced_prefix"])
+    steps = [int(t) for t in g["forced_steps"]]
+    out = {}
+    for tag, E in (("cuda", eng), ("oracle", orc)):
+        p = E.open_session()
+        E.append_audio(p, audio)
+        E.encode([p])
+        sids = [p, E.fork_session(p), E.fork_session(p)]
+        E.decode(sids, [prefix] * 3, sot_index=0)
+        rec = [[E.read_logits(s).copy() for s in sids]]
+        E.decode(sids, [[steps[0]], [steps[1]], [steps[2]]])            # the beams diverge
+        rec.append([E.read_logits(s).copy() for s in sids])
+        E.gather_decoder(sids, [2, 0, 0])                               # row 0 <- 2, rows 1 and 2 <- old row 0
+        E.decode(sids, [[steps[3]], [steps[4]], [steps[3]]])
+        rec.append([E.read_logits(s).copy() for s in sids])
+        frames = [r[2] for r in E.greedy_and_align(sids)]
+        out[tag] = (rec, frames, sids, p)
+    for a, b in zip(out["cuda"][0], out["oracle"][0]):
+        for x, y in zip(a, b):
+            assert np.abs(x - y).max() < 1e-3
+    assert out["cuda"][1] == out["oracle"][1]
+    # identical beams give identical logits; after the gather rows 1 and 2 share a history but got different tokens
+    rec = out["cuda"][0]
+    assert np.array_equal(rec[0][0], rec[0][1]) and np.array_equal(rec[0][0], rec[0][2])
+    assert not np.allclose(rec[2][1], rec[2][2])
+    sids, p = out["cuda"][2], out["cuda"][3]
+    with pytest.raises(WlkError):
+        eng.close_session(p)                                            # forks still open
+    with pytest.raises(WlkError):
+        eng.append_audio(sids[1], audio[:160])                          # a fork holds no audio
+    with pytest.raises(WlkError):
+        eng.encode([sids[1]])
+    for s in reversed(sids):
+        eng.close_session(s)
+    eng.close()

@@ -64,3 +64,29 @@ def test_transcribe_over_b200_model_equals_reference(name):
     assert hasattr(timing, "_b200_saved")
     from whisperlivekit_b200.localagreement import uninstall_native_timing
     uninstall_native_timing()
+
+
+def test_transcribe_with_beam_search_equals_reference():
+    """whisper.transcribe(beam_size=3): DecodingTask's beam rows (decoding.py:728) become forked sessions and
+    PyTorchInference.rearrange_kv_cache (decoding.py:165-170) lands in gather_decoder; segments, tokens and word
+    timings must equal the reference's over its own torch Whisper."""
+    _import_reference()
+    from oracle import whisper_oracle as wo
+    from whisperlivekit.whisper.transcribe import transcribe
+    from whisperlivekit_b200.localagreement import B200WhisperASR, uninstall_native_timing
+
+    g, dims, sd, audio, heads = case_setup("micro")
+    kw = dict(language="en", initial_prompt="", condition_on_previous_text=True, word_timestamps=True,
+              temperature=(0.0,), beam_size=3, no_speech_threshold=None, logprob_threshold=None,
+              compression_ratio_threshold=None)
+    ref = transcribe(_ref_model(dims, sd, heads), audio, **kw)
+    asr = B200WhisperASR(wo.OracleEngine(dims, sd, heads), lan="en")
+    asr.transcribe_kargs = {k: v for k, v in kw.items() if k in ("temperature", "beam_size", "no_speech_threshold",
+                                                                 "logprob_threshold", "compression_ratio_threshold")}
+    got = asr.transcribe(audio, init_prompt="")
+    uninstall_native_timing()
+    assert [s["tokens"] for s in got["segments"]] == [s["tokens"] for s in ref["segments"]]
+    rw = [(w["word"], round(w["start"], 2), round(w["end"], 2)) for s in ref["segments"] for w in s["words"]]
+    gw = [(w["word"], round(w["start"], 2), round(w["end"], 2)) for s in got["segments"] for w in s["words"]]
+    assert gw == rw
+    assert len(asr.model._forks) == 2 and asr.model.gathers > 0

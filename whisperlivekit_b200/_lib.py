@@ -55,6 +55,8 @@ SIGNATURES = {
     "wlk_session_clear_audio": (C.c_int, [_vp, C.c_int32]),
     "wlk_session_audio_len": (C.c_int, [_vp, C.c_int32, _i64p]),
     "wlk_session_reset_decoder": (C.c_int, [_vp, C.c_int32]),
+    "wlk_session_fork": (C.c_int, [_vp, C.c_int32, _vp]),
+    "wlk_sessions_gather_decoder": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "wlk_encode": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "wlk_decode": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int32]),
     "wlk_encode_mel": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32]),

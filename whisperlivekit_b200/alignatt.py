@@ -318,6 +318,20 @@ class _Logits:
         return self.engine.read_logits(self.sid)[None]
 
 
+class _BeamInference:
+    """The one thing whisper.decoding.BeamSearchDecoder asks of its ``inference`` (decoding.py:361):
+    re-index the self-attention K/V rows after ranking (reference simul_whisper/beam.py:15-19)."""
+
+    def __init__(self, hooks):
+        self.hooks = hooks
+        self.kv_cache = {}
+
+    def rearrange_kv_cache(self, source_indices):
+        src = [int(i) for i in source_indices]
+        if src != list(range(len(src))):
+            self.hooks.engine.gather_decoder(self.hooks.beam_sids, src)
+
+
 class AlignAttHooks:
     """Engine-backed implementation of every abstract hook of the reference's AlignAttBase
     (align_att_base.py:541-649).  Mixed in front of AlignAttBase by plugin.make_b200_alignatt_class();
@@ -338,7 +352,8 @@ class AlignAttHooks:
 
     def __del__(self):
         try:
-            self.engine.close_session(self.sid)
+            for sid in reversed(getattr(self, "beam_sids", [self.sid])):     # forks before their parent
+                self.engine.close_session(sid)
         except Exception:
             pass
 
@@ -370,8 +385,19 @@ class AlignAttHooks:
         self.init_tokens()
         self.init_context()
         self.state.decoder_type = cfg.decoder_type
-        if cfg.decoder_type != "greedy":
-            raise NotImplementedError("the B200 AlignAtt backend implements greedy decoding (beams=1)")
+        self.beam, self.beam_sids = 1, [self.sid]
+        if cfg.decoder_type == "beam":
+            # reference simul_whisper.py:182-192: beam_size decoder rows over ONE encoder output.  Here every beam
+            # row is a session forked from the stream's session (shared encoder output / cross-K/V), ranked by the
+            # reference's own BeamSearchDecoder on the host.
+            from whisperlivekit.whisper.decoding import BeamSearchDecoder
+            self.beam = int(cfg.beam_size)
+            self.beam_sids = [self.sid] + [self.engine.fork_session(self.sid) for _ in range(self.beam - 1)]
+            self.state.inference = _BeamInference(self)
+            self.state.token_decoder = BeamSearchDecoder(inference=self.state.inference, eot=self.tokenizer.eot,
+                                                         beam_size=self.beam)
+        elif cfg.decoder_type != "greedy":
+            raise NotImplementedError(f"decoder_type {cfg.decoder_type!r}")
 
     def init_tokens(self):
         import torch
@@ -424,8 +450,10 @@ class AlignAttHooks:
     def _current_tokens(self):
         import torch
         toks = self.state.tokens
+        if toks[0].shape[0] == 1 and self.beam > 1:                          # simul_whisper.py:240-243
+            toks[0] = toks[0].repeat_interleave(self.beam, dim=0)
         if not self.state.context.is_empty():
-            toks = [self.state.context.as_tensor_beam(1, device="cpu")] + toks
+            toks = [self.state.context.as_tensor_beam(self.beam, device="cpu")] + toks
         return torch.cat(toks, dim=1) if len(toks) > 1 else toks[0]
 
     def fire_at_boundary(self, feature):
@@ -461,13 +489,20 @@ class AlignAttHooks:
         return [toks[int(np.argmax(sel))]], [probs]
 
     def _clean_cache(self):
-        self.engine.reset_decoder(self.sid)
+        for sid in self.beam_sids:
+            self.engine.reset_decoder(sid)
+        if self.beam > 1:
+            self.state.token_decoder.reset()                                 # decoder_state.py:55-59
 
     def _init_sum_logprobs(self):
+        if self.beam > 1:
+            import torch
+            return torch.zeros(self.beam)                                    # simul_whisper.py:354-355
         return [0.0]
 
     def _get_logits_and_cross_attn(self, tokens, encoder_feature):
-        self.engine.decode([self.sid], [tokens[0].tolist()], sot_index=self.state.sot_index)
+        rows = [tokens[b].tolist() for b in range(self.beam)] if self.beam > 1 else [tokens[0].tolist()]
+        self.engine.decode(self.beam_sids, rows, sot_index=self.state.sot_index)
         self._iters += 1
         return _Logits(self.engine, self.sid), self._iters
 
@@ -477,21 +512,35 @@ class AlignAttHooks:
         return False
 
     def _suppress_blank_tokens(self, logits):
-        self.engine.suppress([self.sid], self._blank)
+        self.engine.suppress(self.beam_sids, self._blank)
         return logits
 
     def _apply_token_suppression(self, logits):
-        self.engine.suppress([self.sid], self._suppress)
+        self.engine.suppress(self.beam_sids, self._suppress)
         return logits
 
     def _apply_dry_penalty(self, logits, current_tokens):
+        # the reference scans beam row 0 and penalises that token set on every row (align_att_base.py:501,535)
         pen = dry_penalties(current_tokens[0].tolist(), self.tokenizer.eot)
         if pen:
-            self.engine.add_logit_bias(self.sid, [t for t, _ in pen], [-a for _, a in pen])
+            for sid in self.beam_sids:
+                self.engine.add_logit_bias(sid, [t for t, _ in pen], [-a for _, a in pen])
         return logits
+
+    def _update_tokens_beam(self, current_tokens, sum_logprobs):
+        """whisper/decoding.py:317-376 (BeamSearchDecoder.update, unchanged, on the host) over the beams' fp32
+        logits; its rearrange_kv_cache lands in wlk_sessions_gather_decoder.  The attended frames come from each
+        row's own alignment history, which the reference does not re-index either."""
+        import torch
+        res = self.engine.greedy_and_align(self.beam_sids, window_iters=16)
+        self._frames = [int(r[2]) for r in res]
+        lg = torch.from_numpy(np.stack([self.engine.read_logits(sid) for sid in self.beam_sids]))
+        return self.state.token_decoder.update(current_tokens, lg, sum_logprobs)
 
     def _update_tokens(self, current_tokens, logits, sum_logprobs):
         import torch
+        if self.beam > 1:
+            return self._update_tokens_beam(current_tokens, sum_logprobs)
         tok, lp, frame = self.engine.greedy_and_align([self.sid], window_iters=16)[0]
         eot = self.tokenizer.eot
         if int(current_tokens[0, -1]) == eot:                       # decoding.py:280-282
@@ -503,9 +552,11 @@ class AlignAttHooks:
         return tokens, tok == eot
 
     def _process_cross_attention(self, accumulated_cross_attns, content_mel_len):
-        return self._frame                                          # computed with the token, one D2H for both
+        return self._frames if self.beam > 1 else self._frame       # computed with the token, one D2H for both
 
     def _get_attended_frames(self, attn):
+        if self.beam > 1:
+            return list(attn), int(attn[0])                         # simul_whisper.py:435-437
         return [int(attn)], int(attn)
 
     def _is_special_token(self, current_tokens):
@@ -520,7 +571,8 @@ class AlignAttHooks:
 
     def _make_new_tokens_tensor(self, hypothesis):
         import torch
-        return torch.tensor([hypothesis], dtype=torch.long)
+        t = torch.tensor([hypothesis], dtype=torch.long)
+        return t.repeat_interleave(self.beam, dim=0) if self.beam > 1 else t      # simul_whisper.py:450-455
 
     def _evaluate(self, tensor):
         pass

@@ -69,6 +69,8 @@ struct Session {
     bool encoded = false;
     std::vector<int> iter_row_start;
     size_t bytes = 0;
+    int parent = -1;      // >= 0: a beam fork -- audio/mel are null, xa / cross_kv alias the parent's buffers
+    int n_forks = 0;      // open forks reading this session's encoder output
 };
 
 struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; };
@@ -105,6 +107,7 @@ struct wlk_engine {
     int64_t* pad_rows_dev = nullptr;          // rows of h1 to re-zero after the conv1 GEMM
     void** xptrs_dev = nullptr;               // x + b*1500*d
     float* audio_scratch = nullptr;
+    void* beam_scratch = nullptr; size_t beam_scratch_cap = 0;   // staging for wlk_sessions_gather_decoder
     float* mel_scratch = nullptr;             // fp32 [MEL_ROWS][n_mels] for the read_mel tap
     // decoder workspace
     int dec_rows_max = 0;
@@ -408,6 +411,13 @@ Session& get_session(wlk_engine* e, int32_t sid) {
     WLK_CHECK(sid >= 0 && sid < (int)e->sess.size() && e->sess[sid].open, "invalid session id %d", sid);
     return e->sess[sid];
 }
+// the session whose encoder output / cross-K/V / content length `s` decodes against (itself unless a beam fork)
+Session& enc_owner(wlk_engine* e, Session& s) { return s.parent >= 0 ? e->sess[s.parent] : s; }
+Session& get_root_session(wlk_engine* e, int32_t sid, const char* what) {
+    Session& s = get_session(e, sid);
+    WLK_CHECK(s.parent < 0, "session %d is a beam fork of session %d: %s belongs to the parent", sid, s.parent, what);
+    return s;
+}
 
 // ---------------------------------------------------------------------------------------
 // encode: log-mel -> conv stem -> L encoder blocks -> ln_post -> cross-K/V for every decoder layer
@@ -424,7 +434,7 @@ void encode_batch(wlk_engine* e, const int32_t* sids, int n, int32_t* content_ou
     MelJob* mj_dev; MelJob* mj = sg.host<MelJob>(n, &mj_dev);
     void** xkv_dev; void** xkv = sg.host<void*>(n, &xkv_dev);
     for (int i = 0; i < n; ++i) {
-        Session& s = get_session(e, sids[i]);
+        Session& s = get_root_session(e, sids[i], "encode");
         WLK_CHECK(s.audio_len > 0, "session %d has no audio", sids[i]);
         for (int j = 0; j < i; ++j) WLK_CHECK(sids[j] != sids[i], "session %d appears twice in the batch", sids[i]);
         const int64_t N = s.audio_len;
@@ -528,6 +538,9 @@ void run_encoder(wlk_engine* e, const int32_t* sids, int n, void** xkv_dev) {
     for (int i = 0; i < n; ++i) {
         Session& s = e->sess[sids[i]];
         s.self_len = 0; s.align_rows = 0; s.iter_row_start.clear(); s.encoded = true;
+        if (s.n_forks)                                   // a new epoch for the beams of this stream as well
+            for (auto& f : e->sess)
+                if (f.open && f.parent == sids[i]) { f.self_len = 0; f.align_rows = 0; f.iter_row_start.clear(); }
     }
 }
 
@@ -557,14 +570,14 @@ void decode_batch(wlk_engine* e, const int32_t* sids, int n, const int32_t* toke
     for (int i = 0; i < n; ++i) {
         Session& s = get_session(e, sids[i]);
         for (int j = 0; j < i; ++j) WLK_CHECK(sids[j] != sids[i], "session %d appears twice in the batch", sids[i]);
-        WLK_CHECK(s.encoded, "session %d: decode before encode", sids[i]);
+        WLK_CHECK(enc_owner(e, s).encoded, "session %d: decode before encode", sids[i]);
         const int tq = offsets[i + 1] - offsets[i];
         WLK_CHECK(tq >= 1, "session %d: empty token list", sids[i]);
         if (tq > max_tq) max_tq = tq;
         WLK_CHECK(s.self_len + tq <= ctx, "session %d: %d + %d tokens exceed n_text_ctx %d", sids[i], s.self_len, tq, ctx);
         const bool first = s.iter_row_start.empty();
         if (first) WLK_CHECK(sot_index >= 0 && sot_index < tq, "sot_index %d outside the %d fed tokens", sot_index, tq);
-        dj[i].self_kv = s.self_kv; dj[i].cross_kv = s.cross_kv; dj[i].align = s.align;
+        dj[i].self_kv = s.self_kv; dj[i].cross_kv = enc_owner(e, s).cross_kv; dj[i].align = s.align;
         dj[i].logits_last = s.logits_last; dj[i].logits_sot = s.logits_sot;
         dj[i].row_off = r; dj[i].n_rows = tq; dj[i].offset = s.self_len; dj[i].align_row0 = s.align_rows;
         dj[i].slot = sids[i]; dj[i].pad0 = dj[i].pad1 = dj[i].pad2 = 0;
@@ -670,7 +683,7 @@ LogitJob make_logit_job(wlk_engine* e, Session& s, int window_iters, int full) {
     const int first = ni > window_iters ? ni - window_iters : 0;
     j.row_begin = ni ? s.iter_row_start[first] : 0;
     j.row_end = s.align_rows;
-    j.content_len = s.content_len;
+    j.content_len = enc_owner(e, s).content_len;
     j.full = full;
     return j;
 }
@@ -700,11 +713,39 @@ void alloc_session(wlk_engine* e, Session& s) {
     }
 }
 void free_session(wlk_engine* e, Session& s) {
+    if (s.parent >= 0) {                                  // a fork owns its decoder-side buffers only
+        e->sess[s.parent].n_forks -= 1;
+        s.xa = nullptr; s.cross_kv = nullptr;
+    }
     void* ptrs[] = {s.audio, s.mel_raw, s.mel_blockmax, s.xa, s.cross_kv, s.self_kv, s.align, s.logits_last,
                     s.logits_sot, s.attn_out, s.stats};
     for (void* p : ptrs) if (p) cudaFree(p);
     e->bytes_sessions -= s.bytes;
     s = Session{};
+}
+// a beam: decoder-side buffers of its own, encoder output and cross-K/V of `parent` (reference: beam_size decoder rows
+// over one encoder output, simul_whisper.py:240-243)
+void alloc_fork(wlk_engine* e, Session& s, int parent) {
+    const wlk_dims& D = e->dims;
+    const size_t es = e->es();
+    Session& p = e->sess[parent];
+    size_t* acct = &s.bytes;
+    s.bytes = 0;
+    s.self_kv = dmalloc_bytes((size_t)D.n_text_layer * 2 * D.n_text_ctx * D.n_text_state * es, acct);
+    s.align = dmalloc<float>(e, (size_t)(e->n_align > 0 ? e->n_align : 1) * D.n_text_ctx * N_CTX, acct);
+    s.logits_last = dmalloc<float>(e, D.n_vocab, acct);
+    s.logits_sot = dmalloc<float>(e, D.n_vocab, acct);
+    s.attn_out = dmalloc<float>(e, (size_t)D.n_text_ctx * N_CTX, acct);
+    s.stats = dmalloc<float>(e, (size_t)(e->n_align > 0 ? e->n_align : 1) * N_CTX * 2, acct);
+    s.xa = p.xa; s.cross_kv = p.cross_kv; s.parent = parent;
+    p.n_forks += 1;
+    e->bytes_sessions += s.bytes;
+    if (e->act == DT_BF16) {
+        alignas(64) uint8_t tmap[128];
+        make_cross_kv_tmap(tmap, p.cross_kv, D.n_text_layer, D.n_text_head);
+        const size_t slot = (size_t)(&s - e->sess.data());
+        CUDA_CHECK(cudaMemcpy(e->kv_maps_dev + slot * 128, tmap, 128, cudaMemcpyHostToDevice));
+    }
 }
 
 void create_engine(const wlk_dims* dims, const wlk_config* cfg, wlk_engine** out) {
@@ -805,8 +846,9 @@ void create_engine(const wlk_dims* dims, const wlk_config* cfg, wlk_engine** out
 
 void destroy_engine(wlk_engine* e) {
     cudaStreamSynchronize(e->st);
+    for (auto& s : e->sess) if (s.open && s.parent >= 0) free_session(e, s);     // forks before their parents
     for (auto& s : e->sess) if (s.open) free_session(e, s);
-    void* ptrs[] = {e->arena.base, e->stage_f32, e->mel_t, e->h1, e->x, e->xn, e->qkv, e->att, e->hid, e->audio_scratch, e->mel_scratch,
+    void* ptrs[] = {e->arena.base, e->stage_f32, e->mel_t, e->h1, e->x, e->xn, e->qkv, e->att, e->hid, e->audio_scratch, e->mel_scratch, e->beam_scratch,
                     e->pad_rows_dev, e->xptrs_dev, e->dx, e->dxn, e->dq, e->datt, e->dhid, e->dsel, e->stg_dev,
                     e->res_dev, e->align_rank_dev, e->kv_maps_dev, e->all_logits_dev};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -957,14 +999,71 @@ int wlk_session_close(wlk_engine* e, int32_t sid) {
     WLK_API_BEGIN
     LOCK(e);
     Session& s = get_session(e, sid);
+    WLK_CHECK(s.n_forks == 0, "session %d still has %d beam fork(s): close them first", sid, s.n_forks);
     CUDA_CHECK(cudaStreamSynchronize(e->st));
     free_session(e, s);
+    WLK_API_END
+}
+int wlk_session_fork(wlk_engine* e, int32_t parent, int32_t* child) {
+    WLK_API_BEGIN
+    LOCK(e);
+    WLK_CHECK(child, "null out pointer");
+    get_root_session(e, parent, "forking");
+    int found = -1;
+    for (int i = 0; i < (int)e->sess.size(); ++i) if (!e->sess[i].open) { found = i; break; }
+    WLK_CHECK(found >= 0, "all %d sessions in use", (int)e->sess.size());
+    alloc_fork(e, e->sess[found], parent);
+    e->sess[found].open = true;
+    *child = found;
+    WLK_API_END
+}
+int wlk_sessions_gather_decoder(wlk_engine* e, const int32_t* sids, const int32_t* src, int n) {
+    WLK_API_BEGIN
+    LOCK(e);
+    WLK_CHECK(sids && src && n >= 1, "bad argument");
+    const wlk_dims& D = e->dims;
+    const size_t es = e->es();
+    const size_t pitch = (size_t)D.n_text_ctx * 64 * es;                 // one (layer, k|v, head) plane of the self-K/V
+    const size_t planes = (size_t)D.n_text_layer * 2 * D.n_text_head;
+    std::vector<int> moved;
+    for (int i = 0; i < n; ++i) {
+        Session& d = get_session(e, sids[i]);
+        WLK_CHECK(src[i] >= 0 && src[i] < n, "source index %d out of range", src[i]);
+        Session& s = get_session(e, sids[src[i]]);
+        WLK_CHECK(&enc_owner(e, d) == &enc_owner(e, s), "sessions %d and %d do not share an encoder output", sids[i], sids[src[i]]);
+        for (int j = 0; j < i; ++j) WLK_CHECK(sids[j] != sids[i], "session %d appears twice", sids[i]);
+        if (src[i] != i) moved.push_back(i);
+    }
+    if (moved.empty()) return 0;
+    const size_t per = planes * pitch;
+    if (e->beam_scratch_cap < moved.size() * per) {
+        if (e->beam_scratch) { CUDA_CHECK(cudaStreamSynchronize(e->st)); cudaFree(e->beam_scratch); e->beam_scratch = nullptr; }
+        CUDA_CHECK(cudaMalloc(&e->beam_scratch, moved.size() * per));
+        e->beam_scratch_cap = moved.size() * per;
+    }
+    // stage every source that moves (only its valid prefix), then scatter: sources may be overwritten by other moves
+    std::vector<int> new_len(n);
+    for (int i = 0; i < n; ++i) new_len[i] = e->sess[sids[src[i]]].self_len;
+    for (size_t k = 0; k < moved.size(); ++k) {
+        Session& s = e->sess[sids[src[moved[k]]]];
+        if (s.self_len)
+            CUDA_CHECK(cudaMemcpy2DAsync((char*)e->beam_scratch + k * per, pitch, s.self_kv, pitch, (size_t)s.self_len * 64 * es,
+                                         planes, cudaMemcpyDeviceToDevice, e->st));
+    }
+    for (size_t k = 0; k < moved.size(); ++k) {
+        Session& d = e->sess[sids[moved[k]]];
+        const int len = new_len[moved[k]];
+        if (len)
+            CUDA_CHECK(cudaMemcpy2DAsync(d.self_kv, pitch, (char*)e->beam_scratch + k * per, pitch, (size_t)len * 64 * es, planes,
+                                         cudaMemcpyDeviceToDevice, e->st));
+    }
+    for (int i = 0; i < n; ++i) e->sess[sids[i]].self_len = new_len[i];
     WLK_API_END
 }
 int wlk_session_append_audio(wlk_engine* e, int32_t sid, const float* pcm, int64_t n) {
     WLK_API_BEGIN
     LOCK(e);
-    Session& s = get_session(e, sid);
+    Session& s = get_root_session(e, sid, "the audio ring");
     WLK_CHECK(n >= 0 && (n == 0 || pcm), "bad audio chunk");
     WLK_CHECK(s.audio_len + n <= AUDIO_CAP, "audio buffer overflow: %lld + %lld > %d samples", (long long)s.audio_len, (long long)n, AUDIO_CAP);
     if (n) CUDA_CHECK(cudaMemcpyAsync(s.audio + s.audio_len, pcm, (size_t)n * 4, cudaMemcpyHostToDevice, e->st));
@@ -974,7 +1073,7 @@ int wlk_session_append_audio(wlk_engine* e, int32_t sid, const float* pcm, int64
 int wlk_session_drop_audio(wlk_engine* e, int32_t sid, int64_t n) {
     WLK_API_BEGIN
     LOCK(e);
-    Session& s = get_session(e, sid);
+    Session& s = get_root_session(e, sid, "the audio ring");
     WLK_CHECK(n >= 0 && n <= s.audio_len, "cannot drop %lld of %lld samples", (long long)n, (long long)s.audio_len);
     const int64_t keep = s.audio_len - n;
     if (n && keep) {
@@ -1023,7 +1122,7 @@ int wlk_decode(wlk_engine* e, const int32_t* sids, int n, const int32_t* tokens,
 int wlk_encode_mel(wlk_engine* e, int32_t sid, const float* mel_host, int32_t content_mel_len) {
     WLK_API_BEGIN
     LOCK(e);
-    Session& s = get_session(e, sid);
+    Session& s = get_root_session(e, sid, "encode");
     WLK_CHECK(mel_host && content_mel_len >= 0, "bad arguments");
     const int nm = e->dims.n_mels;
     Stager sg(e);
@@ -1154,7 +1253,7 @@ int wlk_greedy_and_align(wlk_engine* e, const int32_t* sids, int n, int32_t wind
 int wlk_read_mel(wlk_engine* e, int32_t sid, float* out) {
     WLK_API_BEGIN
     LOCK(e);
-    Session& s = get_session(e, sid);
+    Session& s = get_root_session(e, sid, "the mel");
     WLK_CHECK(out && s.encoded, "session not encoded");
     const int nm = e->dims.n_mels;
     // re-run the finalize pass into an fp32 time-major scratch (att is free between calls)
@@ -1178,7 +1277,7 @@ int wlk_read_mel(wlk_engine* e, int32_t sid, float* out) {
 int wlk_read_encoder(wlk_engine* e, int32_t sid, float* out) {
     WLK_API_BEGIN
     LOCK(e);
-    Session& s = get_session(e, sid);
+    Session& s = enc_owner(e, get_session(e, sid));
     WLK_CHECK(out && s.encoded, "session not encoded");
     const size_t n = (size_t)N_CTX * e->dims.n_audio_state;
     float* h = tap_buffer(e, n);

@@ -122,6 +122,19 @@ class WhisperEngine:
         L.check(self.lib.wlk_session_reset_decoder(self.h, sid))
 
     # -- hot path --------------------------------------------------------------------
+    def fork_session(self, parent: int) -> int:
+        """A beam of ``parent``: own self-K/V, logits and alignment rows; shared encoder output and cross-K/V."""
+        sid = C.c_int32()
+        L.check(self.lib.wlk_session_fork(self.h, parent, C.byref(sid)))
+        return sid.value
+
+    def gather_decoder(self, sids: Sequence[int], source_indices: Sequence[int]) -> None:
+        """BeamPyTorchInference.rearrange_kv_cache (reference beam.py:15-19) over a group of sessions."""
+        a, b = _i32(sids), _i32(source_indices)
+        if len(a) != len(b):
+            raise ValueError("sids and source_indices differ in length")
+        L.check(self.lib.wlk_sessions_gather_decoder(self.h, _ptr(a), _ptr(b), len(a)))
+
     def encode(self, sids: Sequence[int]) -> List[int]:
         s = _i32(sids)
         out = np.zeros(len(s), np.int32)

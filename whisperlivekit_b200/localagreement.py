@@ -47,14 +47,29 @@ class AudioFeatures:
         return self
 
     def repeat_interleave(self, n, dim=0):
-        if n != 1:
-            raise NotImplementedError("B200 LocalAgreement model: beam search / best_of > 1 not supported yet")
-        return self
+        return self          # beam_size / best_of rows all read the one encoder output (forked sessions)
 
     def to(self, *a, **k):
         return self
 
     def half(self):
+        return self
+
+
+class _KvHandle:
+    """Stand-in for a self-attention K/V cache tensor inside the reference's ``kv_cache`` dict.  The only thing
+    the reference does with it is ``kv_cache[id] = kv_cache[id][source_indices].detach()``
+    (PyTorchInference.rearrange_kv_cache, decoding.py:165-170): indexing records the permutation, which the model
+    applies on the device (wlk_sessions_gather_decoder) before the next decoder call."""
+
+    def __init__(self, model):
+        self.model = model
+
+    def __getitem__(self, source_indices):
+        self.model._pending_perm = [int(i) for i in source_indices]
+        return self
+
+    def detach(self):
         return self
 
 
@@ -117,6 +132,9 @@ class B200TranscribeModel:
         self._last_mel = None
         self.encoder_calls = 0
         self.encoder_reuses = 0
+        self._forks: List[int] = []            # beam_size / best_of rows beyond the first: sessions forked from self.sid
+        self._pending_perm = None
+        self.gathers = 0
         self._decode_fn, self._detect_fn, self._transcribe_fn = decode_function, detect_language_function, transcribe_function
 
     # -- attributes the reference reads ---------------------------------------------------
@@ -158,23 +176,42 @@ class B200TranscribeModel:
 
     embed_audio = encoder
 
+    def _rows(self, n: int) -> List[int]:
+        """Sessions behind the n decoder rows of a beam / best_of group (decoding.py:728): row 0 is the segment's
+        session, the others are forks sharing its encoder output and cross-K/V."""
+        while len(self._forks) < n - 1:
+            self._forks.append(self.engine.fork_session(self.sid))
+        return [self.sid] + self._forks[: n - 1]
+
     def _decode(self, tokens, xa, kv_cache):
         import torch
-        if tokens.shape[0] != 1:
-            raise NotImplementedError("B200 LocalAgreement model: beam search / best_of > 1 not supported yet")
-        toks = [int(t) for t in tokens[0].tolist()]
+        B = int(tokens.shape[0])
+        sids = self._rows(B)
+        rows = [[int(t) for t in tokens[b].tolist()] for b in range(B)]
         fresh = kv_cache is None or len(kv_cache) == 0
         if fresh:
-            self.engine.reset_decoder(self.sid)
+            for sid in sids:
+                self.engine.reset_decoder(sid)
+            self._pending_perm = None
             if kv_cache is not None:
                 kv_cache["b200_session"] = self.sid
+                for blk in self.decoder.blocks:                     # what rearrange_kv_cache will index
+                    kv_cache[blk.attn.key_cache_id] = _KvHandle(self)
+                    kv_cache[blk.attn.value_cache_id] = _KvHandle(self)
+        elif self._pending_perm is not None:
+            if self._pending_perm != list(range(B)):
+                self.engine.gather_decoder(sids, self._pending_perm)
+                self.gathers += 1
+            self._pending_perm = None
         sot = self.engine.specials.sot
-        sot_index = toks.index(sot) if (fresh and sot in toks) else 0
-        self.engine.decode([self.sid], [toks], sot_index=sot_index)
-        logits = torch.zeros(1, len(toks), self.dims.n_vocab)
-        logits[0, -1] = torch.from_numpy(self.engine.read_logits(self.sid))
-        if fresh and len(toks) > 1:
-            logits[0, sot_index] = torch.from_numpy(self.engine.read_sot_logits(self.sid))
+        sot_index = rows[0].index(sot) if (fresh and sot in rows[0]) else 0
+        self.engine.decode(sids, rows, sot_index=sot_index)
+        T = len(rows[0])
+        logits = torch.zeros(B, T, self.dims.n_vocab)
+        for b, sid in enumerate(sids):
+            logits[b, -1] = torch.from_numpy(self.engine.read_logits(sid))
+            if fresh and T > 1:
+                logits[b, sot_index] = torch.from_numpy(self.engine.read_sot_logits(sid))
         return logits
 
     def logits(self, tokens, audio_features, kv_cache=None, return_cross_attn=False):
@@ -205,6 +242,9 @@ class B200TranscribeModel:
         return torch.from_numpy(all_logits)[None]
 
     def close(self):
+        for sid in reversed(self._forks):
+            self.engine.close_session(sid)
+        self._forks = []
         self.engine.close_session(self.sid)
 
 
