@@ -38,6 +38,7 @@ class WhisperEngine:
         self.dims = dims
         self.specials = SpecialTokens.for_dims(dims)
         self.precision = precision
+        self.device = int(device)
         heads = list(align_heads) if align_heads is not None else default_alignment_heads(dims)
         self.align_heads = [tuple(int(v) for v in h) for h in heads]
         be = {"auto": L.BACKEND_AUTO, "simt": L.BACKEND_SIMT, "tcgen05": L.BACKEND_TCGEN05}
