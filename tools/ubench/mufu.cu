@@ -17,6 +17,11 @@ __global__ void __launch_bounds__(512) k(float* out, int iters, float seed) {
             if (OP == 2) asm volatile("max.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(a[(i + 1) & 7]));
             if (OP == 3) { unsigned r; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a[i]), "f"(a[(i + 1) & 7])); a[i] = __uint_as_float(r); }
             if (OP == 4) asm volatile("add.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(a[(i + 1) & 7]));
+            if (OP == 5) { unsigned r = __float_as_uint(a[i]); asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(r)); a[i] = __uint_as_float(r); }
+            if (OP == 6) { unsigned r = __float_as_uint(a[i]); asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(r)); a[i] = __uint_as_float(r); }
+            if (OP == 7) { unsigned r = __float_as_uint(a[i]); asm volatile("fma.rn.bf16x2 %0, %0, %0, %0;" : "+r"(r)); a[i] = __uint_as_float(r); }
+            if (OP == 8) { unsigned r = __float_as_uint(a[i]), q = __float_as_uint(a[(i + 1) & 7]); asm volatile("max.bf16x2 %0, %0, %1;" : "+r"(r) : "r"(q)); a[i] = __uint_as_float(r); }
+            if (OP == 9) { unsigned r = __float_as_uint(a[i]); asm volatile("tanh.approx.bf16x2 %0, %0;" : "+r"(r)); a[i] = __uint_as_float(r); }
         }
     }
     float s = 0;
@@ -45,6 +50,7 @@ void run(const char* name, int threads) {
 int main() {
     for (int t : {128, 256, 512}) {
         run<0>("ex2", t); run<1>("ffma", t); run<2>("fmnmx", t); run<3>("f2fp", t); run<4>("fadd", t);
+        run<5>("ex2bf16x2", t); run<6>("ex2f16x2", t); run<7>("hfma2bf16", t); run<8>("hmnmx2bf16", t); run<9>("tanhbf16x2", t);
     }
     return 0;
 }
