@@ -88,6 +88,11 @@ struct wlk_engine {
     int num_sms = 148;
     cudaStream_t st = nullptr;
     std::mutex mu;
+    // token-step CUDA graphs: the ~390 launches of one decoder step depend only on the batch size (every per-session
+    // quantity travels in the staged job arrays), so they are captured once per batch size and replayed
+    bool graphs_on = true;
+    std::map<uint64_t, cudaGraphExec_t> dec_graphs;
+    std::set<uint64_t> dec_graph_seen;
 
     Arena arena;
     Weights w;
@@ -592,6 +597,7 @@ void decode_batch(wlk_engine* e, const int32_t* sids, int n, const int32_t* toke
     }
     sg.upload();
 
+    auto launch_all = [&]() {
     {   ProfScope ps(e, WLK_KC_MISC);
         embed_tokens(tok_dev, pos_dev, W.emb_f32, W.dec_pos, e->dx, R, dt, e->st); }
     const float qk_scale = powf(64.0f, -0.25f);
@@ -666,6 +672,44 @@ void decode_batch(wlk_engine* e, const int32_t* sids, int n, const int32_t* toke
         g.epi.mode = EPI_ROWPTR; g.epi.batch_ptrs = lptr_dev; g.epi.rows_per_batch = 1; g.epi.c_type = DT_F32;
         g.epi.ldc = D.n_vocab;
         run_gemm(e, g, WLK_KC_LOGITS); }
+    };   // launch_all
+
+    // Token steps (one row per session): replay a captured graph.  The key is everything that shapes the launches --
+    // batch size and number of logits rows; pointers into the staging block are a function of those two.  A key is
+    // run eagerly the first time (lazy one-time initialisations happen outside capture) and captured the second.
+    const bool graphable = e->graphs_on && max_tq == 1 && !all_logits_dev && !e->prof_on;
+    if (!graphable) {
+        launch_all();
+    } else {
+        const uint64_t key = ((uint64_t)n << 32) | (uint32_t)n_sel;
+        auto it = e->dec_graphs.find(key);
+        if (it == e->dec_graphs.end() && !e->dec_graph_seen.count(key)) {
+            e->dec_graph_seen.insert(key);
+            launch_all();
+        } else {
+            if (it == e->dec_graphs.end()) {
+                cudaGraph_t graph = nullptr;
+                CUDA_CHECK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeRelaxed));
+                try {
+                    launch_all();
+                } catch (...) {
+                    cudaStreamEndCapture(e->st, &graph);
+                    if (graph) cudaGraphDestroy(graph);
+                    throw;
+                }
+                CUDA_CHECK(cudaStreamEndCapture(e->st, &graph));
+                cudaGraphExec_t exec = nullptr;
+                CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+                cudaGraphDestroy(graph);
+                if (e->dec_graphs.size() >= 32) {                // batch sizes seen so far: bound the cache
+                    for (auto& kv : e->dec_graphs) cudaGraphExecDestroy(kv.second);
+                    e->dec_graphs.clear();
+                }
+                it = e->dec_graphs.emplace(key, exec).first;
+            }
+            CUDA_CHECK(cudaGraphLaunch(it->second, e->st));
+        }
+    }
     for (int i = 0; i < n; ++i) {
         Session& s = e->sess[sids[i]];
         const int tq = offsets[i + 1] - offsets[i];
@@ -775,6 +819,7 @@ void create_engine(const wlk_dims* dims, const wlk_config* cfg, wlk_engine** out
                       : (e->act == DT_BF16 ? WLK_BACKEND_TCGEN05 : WLK_BACKEND_SIMT);
     if (e->act != DT_BF16) { e->gemm_backend = WLK_BACKEND_SIMT; e->attn_backend = WLK_BACKEND_SIMT; }
     CUDA_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    {   const char* v = getenv("WLK_GRAPHS"); e->graphs_on = !(v && v[0] == '0'); }
     for (auto& t : e->timers) CUDA_CHECK(cudaEventCreate(&t));
     CUDA_CHECK(cudaEventCreateWithFlags(&e->stg_done, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventRecord(e->stg_done, e->st));
@@ -859,6 +904,7 @@ void destroy_engine(wlk_engine* e) {
     for (auto& p : e->prof) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto& p : e->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (e->stg_done) cudaEventDestroy(e->stg_done);
+    for (auto& kv : e->dec_graphs) cudaGraphExecDestroy(kv.second);
     cudaStreamDestroy(e->st);
     delete e;
 }
