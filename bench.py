@@ -275,6 +275,10 @@ def main():
         value = total_streams * CHUNK_S * args.steps / (ms_dev / 1e3)
         e2e_value = total_streams * CHUNK_S * args.steps / (ms_e2e / 1e3)
         g = prof["gemm_enc"]
+        traffic = None                                     # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
+        tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+        if os.path.exists(tpath) and B == 96 and args.model == "large-v3":
+            traffic = json.load(open(tpath))["mean_dram_bytes_per_launch"]
         ach = g["flops"] / (g["ms"] / 1e3) / 1e12 if g["ms"] else 0.0
         mult = dict(mel=2, align=3)
         launches = int(sum(v["launches"] * mult.get(k, 1) for k, v in prof.items()))
@@ -293,7 +297,9 @@ def main():
             gpu_launches=launches,
             clocks=clocks,
             roofline=dict(bound="tensor", kernel="gemm_tc2_kernel (cta_group::2 pair GEMM; encoder GEMMs, class gemm_enc)", achieved=ach,
-                          peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=ach / peaks["bf16_tflops"], traffic=None,
+                          peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=ach / peaks["bf16_tflops"], traffic=traffic,
+                          traffic_note="dram__bytes_read+write per launch, mean of one encoder layer's 4 GEMMs, ncu --set full at 96 "
+                                       "streams (profiles/r01_gemm_traffic.json); algorithmic 2.04 GB",
                           peak_source=peaks["source"],
                           flops_per_launch=g["flops"] / max(1, g["launches"]), ms_per_launch=g["ms"] / max(1, g["launches"])),
             kernel_classes=classes,

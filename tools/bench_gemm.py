@@ -13,15 +13,17 @@ out_bf16 = os.environ.get("OUT", "bf16") == "bf16"
 gelu = os.environ.get("GELU", "1") == "1"
 eng = WhisperEngine(DIMS["micro"], None, [(0, 0)], precision="bf16", max_sessions=1, max_batch=1)
 A = torch.randn(M, K, device="cuda").bfloat16()
-W = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+ROT = int(os.environ.get("ROTATE", "1"))          # > 1: cycle through that many weight copies (HBM-streaming regime)
+Ws = [(torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16() for _ in range(ROT)]
+W = Ws[0]
 b = torch.randn(N, device="cuda")
 C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16 if out_bf16 else torch.float32)
 torch.cuda.synchronize()
 for _ in range(2):
     eng.op_gemm(os.environ.get("BACKEND", "tcgen05"), A.data_ptr(), 1, K, W.data_ptr(), 1, K, b.data_ptr(), C.data_ptr(), 1 if out_bf16 else 0, N, M, N, K, gelu)
 eng.timer_record(0)
-for _ in range(iters):
-    eng.op_gemm(os.environ.get("BACKEND", "tcgen05"), A.data_ptr(), 1, K, W.data_ptr(), 1, K, b.data_ptr(), C.data_ptr(), 1 if out_bf16 else 0, N, M, N, K, gelu)
+for i in range(iters):
+    eng.op_gemm(os.environ.get("BACKEND", "tcgen05"), A.data_ptr(), 1, K, Ws[i % ROT].data_ptr(), 1, K, b.data_ptr(), C.data_ptr(), 1 if out_bf16 else 0, N, M, N, K, gelu)
 eng.timer_record(1)
 ms = eng.timer_elapsed_ms(0, 1) / iters
-print(f"gemm {M}x{N}x{K} gelu={int(gelu)} out={"bf16" if out_bf16 else "f32"}: {ms:.3f} ms  {2.0*M*N*K/ms/1e9:.1f} TFLOP/s")
+print(f"gemm rot={ROT} {M}x{N}x{K} gelu={int(gelu)} out={"bf16" if out_bf16 else "f32"}: {ms:.3f} ms  {2.0*M*N*K/ms/1e9:.1f} TFLOP/s")

@@ -300,6 +300,15 @@ void gemm_tcgen05(const GemmArgs& g, cudaStream_t st, int num_sms, int variant) 
         gemm_tcgen05_pair(g, st, num_sms);
         return;
     }
+    // tuning hooks (WLK_GEMM_VARIANT): 3 = <64,8>, 4 = <32,10>, 5/6 = <64,8> split-K 2/4, 7/8 = <32,10> split-K 2/4
+    if (variant >= 3 && variant <= 8) {
+        const int num_k = (g.K + BK - 1) / BK;
+        int sp = (variant == 5 || variant == 7) ? 2 : (variant == 6 || variant == 8) ? 4 : 1;
+        if (sp > num_k / 2) sp = 1;
+        if (variant == 3 || variant == 5 || variant == 6) launch<64, 8>(g, st, num_sms, sp);
+        else launch<32, 10>(g, st, num_sms, sp);
+        return;
+    }
     const int tiles256 = ((g.M + BM - 1) / BM) * ((g.N + 255) / 256);
     if (g.N >= 256 && tiles256 >= num_sms) launch<256, 4>(g, st, num_sms);
     else if (g.N >= 128 && ((g.M + BM - 1) / BM) * ((g.N + 127) / 128) >= num_sms / 2) launch<128, 6>(g, st, num_sms);
