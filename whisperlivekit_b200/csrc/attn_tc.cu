@@ -331,11 +331,9 @@ void enc_attention_tcgen05(const void* qkv, int batch, int n_head, int d_model, 
     std::string err;
     WLK_CHECK(make_tmap_bf16_2d(&tm, qkv, (uint64_t)batch * N_CTX, (uint64_t)3 * d_model, (uint64_t)3 * d_model, BQ, DH, &err),
               "qkv tensor map: %s", err.c_str());
-    static bool set = false;
-    if (!set) {
+    static bool seen[64] = {};
+    if (first_on_device(seen))
         CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-        set = true;
-    }
     dim3 grid((N_CTX + BQ - 1) / BQ, n_head, batch);
     attn_tc_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm, nullptr, nullptr, 0, nullptr, n_head, d_model,
                                                               reinterpret_cast<bf16*>(out));
@@ -357,11 +355,9 @@ void dec_cross_attention_tcgen05(const void* q, int total_rows, const DecJob* jo
     std::string err;
     WLK_CHECK(make_tmap_bf16_2d(&tm, q, (uint64_t)total_rows, (uint64_t)d_model, (uint64_t)d_model, BQ, DH, &err),
               "query tensor map: %s", err.c_str());
-    static bool set = false;
-    if (!set) {
+    static bool seen[64] = {};
+    if (first_on_device(seen))
         CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-        set = true;
-    }
     dim3 grid((max_rows + BQ - 1) / BQ, n_head, n_jobs);
     CUDA_CHECK(launch_pdl(attn_tc_kernel<true>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM, st, tm,
                           reinterpret_cast<const CUtensorMap*>(kv_maps_dev), jobs, layer, align_rank, n_head, d_model,

@@ -65,6 +65,18 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// True the first time it is called for the current device with this flag array: kernel attributes (dynamic shared
+// memory limits) and scratch allocations are per device, and several engines -- one per GPU -- may live in a process.
+inline bool first_on_device(bool (&seen)[64]) {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (seen[d]) return false;
+    seen[d] = true;
+    return true;
+}
+inline int current_device() { int d = 0; cudaGetDevice(&d); return d & 63; }
+
 enum DType { DT_F32 = 0, DT_BF16 = 1 };
 inline size_t dtype_size(int t) { return t == DT_F32 ? 4 : 2; }
 

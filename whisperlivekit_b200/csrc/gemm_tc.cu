@@ -243,8 +243,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // split-K scratch: fp32 partial tiles + one arrival counter per output tile (zero between launches)
-static float* g_sk_scratch = nullptr;
-static int* g_sk_counters = nullptr;
+// split-K scratch (partial tiles + per-tile ticket counters), one set per device
+static float* g_sk_scratch_dev[64] = {};
+static int* g_sk_counters_dev[64] = {};
 constexpr size_t SK_SCRATCH_FLOATS = (size_t)8 << 20;     // 32 MB
 constexpr int SK_MAX_TILES = 4096;
 
@@ -254,26 +255,25 @@ void launch(const GemmArgs& g, cudaStream_t st, int num_sms, int splits = 1) {
     if (splits > 1) {
         const int tiles_mn = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
         if ((size_t)splits * tiles_mn * BM * BN > SK_SCRATCH_FLOATS || tiles_mn > SK_MAX_TILES) splits = 1;
-        else if (!g_sk_scratch) {
-            CUDA_CHECK(cudaMalloc(&g_sk_scratch, SK_SCRATCH_FLOATS * 4));
-            CUDA_CHECK(cudaMalloc(&g_sk_counters, SK_MAX_TILES * 4));
-            CUDA_CHECK(cudaMemset(g_sk_counters, 0, SK_MAX_TILES * 4));
+        else if (!g_sk_scratch_dev[current_device()]) {
+            const int d = current_device();
+            CUDA_CHECK(cudaMalloc(&g_sk_scratch_dev[d], SK_SCRATCH_FLOATS * 4));
+            CUDA_CHECK(cudaMalloc(&g_sk_counters_dev[d], SK_MAX_TILES * 4));
+            CUDA_CHECK(cudaMemset(g_sk_counters_dev[d], 0, SK_MAX_TILES * 4));
         }
     }
     CUtensorMap tmA, tmW;
     std::string err;
     WLK_CHECK(make_tmap_bf16_2d(&tmA, g.A, g.M, g.K, g.lda, BM, BK, &err), "A tensor map: %s", err.c_str());
     WLK_CHECK(make_tmap_bf16_2d(&tmW, g.W, g.N, g.K, g.ldw, BN, BK, &err), "W tensor map: %s", err.c_str());
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool seen[64] = {};
+    if (first_on_device(seen))
         CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)L::DYN));
-        attr_set = true;
-    }
     const int num_tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * splits;
     const int grid = num_tiles < num_sms ? num_tiles : num_sms;
     CUDA_CHECK(launch_pdl(gemm_tc_kernel<BN, STAGES>, dim3(grid), dim3(NUM_THREADS), L::DYN, st, tmA, tmW, g.M, g.N, g.K, splits,
-                          g_sk_scratch, g_sk_counters, g.epi));
+                          g_sk_scratch_dev[current_device()], g_sk_counters_dev[current_device()], g.epi));
 }
 
 }  // namespace

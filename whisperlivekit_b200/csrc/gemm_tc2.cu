@@ -209,11 +209,9 @@ void gemm_tcgen05_pair(const GemmArgs& g, cudaStream_t st, int num_sms) {
     std::string err;
     WLK_CHECK(make_tmap_bf16_2d(&tmA, g.A, g.M, g.K, g.lda, 128, BK2, &err), "A tensor map: %s", err.c_str());
     WLK_CHECK(make_tmap_bf16_2d(&tmW, g.W, g.N, g.K, g.ldw, 128, BK2, &err), "W tensor map: %s", err.c_str());
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool seen[64] = {};
+    if (first_on_device(seen))
         CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2));
-        attr_set = true;
-    }
     const int num_tiles = ((g.M + BM2 - 1) / BM2) * ((g.N + BN2 - 1) / BN2);
     int clusters = num_sms / 2;
     if (num_tiles < clusters) clusters = num_tiles;

@@ -456,11 +456,10 @@ enc_attn_simt_kernel(const T* __restrict__ qkv, int n_head, int d_model, T* __re
 void enc_attention_simt(const void* qkv, int type, int batch, int n_head, int d_model, void* out, cudaStream_t st) {
     dim3 grid((N_CTX + 63) / 64, n_head, batch);
     const int smem = 4 * 64 * 65 * 4;
-    static bool set = false;
-    if (!set) {
+    static bool seen[64] = {};
+    if (first_on_device(seen)) {
         CUDA_CHECK(cudaFuncSetAttribute(enc_attn_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CUDA_CHECK(cudaFuncSetAttribute(enc_attn_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        set = true;
     }
     if (type == DT_F32) enc_attn_simt_kernel<float><<<grid, 256, smem, st>>>((const float*)qkv, n_head, d_model, (float*)out);
     else enc_attn_simt_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)qkv, n_head, d_model, (bf16*)out);
@@ -742,11 +741,9 @@ static void launch_cross(const void* q, const DecJob* jobs, int n_jobs, int laye
                          const int32_t* align_rank, void* out, int only_align, cudaStream_t st) {
     dim3 grid(n_head, n_jobs);
     const int smem = (QB * N_CTX + QB * 64 + 8 * QB * 64) * 4;
-    static bool set = false;
-    if (!set) {
+    static bool seen[64] = {};
+    if (first_on_device(seen))
         CUDA_CHECK(cudaFuncSetAttribute(dec_cross_attn_kernel<T, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        set = true;
-    }
     CUDA_CHECK(launch_pdl(dec_cross_attn_kernel<T, QB>, grid, dim3(256), (size_t)smem, st, (const T*)q, jobs, layer, n_head, d_model, n_text_ctx, align_rank, (T*)out, only_align));
 }
 void dec_cross_attention(const void* q, int type, const DecJob* jobs, int n_jobs, int layer, int n_head, int d_model,
