@@ -168,6 +168,45 @@ int wlk_profile_class_name(int kernel_class, const char** name);
 enum { WLK_KC_MEL = 0, WLK_KC_GEMM_ENC, WLK_KC_ATTN_ENC, WLK_KC_LN, WLK_KC_GEMM_XKV, WLK_KC_GEMM_DEC,
        WLK_KC_ATTN_DEC_SELF, WLK_KC_ATTN_DEC_CROSS, WLK_KC_LOGITS, WLK_KC_ALIGN, WLK_KC_MISC, WLK_KC_COUNT };
 
+/* =====================================================================================
+ * Qwen3-ASR causal-KV audio tower.  Replaces
+ * QwenAudioCausalKVEncoder (reference third_party/qwen3-asr-causal/src/qwen3_asr_causal/causal.py:60-782):
+ * append-only execution of the pretrained audio tower -- every mel frame transits conv stem and layers exactly
+ * once, per-layer K/V of the bounded left window stay on the device, block-bidirectional or causal mask.
+ * Tensor names are the tower's own state_dict names (conv2d1.weight ... layers.N.self_attn.q_proj.weight ...
+ * ln_post.weight, proj1.weight, proj2.weight), fp32 on the host.
+ * ===================================================================================== */
+typedef struct wlk_qwen wlk_qwen;
+typedef struct {
+    int32_t n_mels;              /* 128 */
+    int32_t conv_channels;       /* conv2d1/2/3 output channels (3x3, stride 2, pad 1) */
+    int32_t d_model, n_head, n_layer, ffn_dim;
+    int32_t out_dim;             /* proj2 output width */
+    int32_t max_positions;       /* rows of the sinusoid table; the closed form is used beyond (causal.py:204-228) */
+    int32_t chunk_frames;        /* 8: mel frames per encoder step */
+    int32_t block_frames;        /* fixed attention block in mel frames (config.py:31-36); 0 = consume per chunk */
+    int32_t left_context_steps;  /* K/V kept per layer (causal.py:103-106) */
+    int32_t block_bidirectional; /* 1: queries see their whole block (causal.py:336-341) */
+    int32_t conv_out_bias;
+} wlk_qwen_dims;
+
+int wlk_qwen_create(const wlk_qwen_dims* dims, const wlk_config* cfg, wlk_qwen** out);
+int wlk_qwen_destroy(wlk_qwen* q);
+int wlk_qwen_load_tensor(wlk_qwen* q, const char* name, const float* host, const int64_t* shape, int ndim);
+int wlk_qwen_finalize_weights(wlk_qwen* q);
+int wlk_qwen_memory(wlk_qwen* q, size_t* weights, size_t* sessions, size_t* workspace);
+/* QwenAudioCausalKVState (causal.py:44-57): pending mel frames, per-layer K/V, emitted steps */
+int wlk_qwen_session_open(wlk_qwen* q, int32_t* sid);
+int wlk_qwen_session_close(wlk_qwen* q, int32_t sid);
+int wlk_qwen_session_reset(wlk_qwen* q, int32_t sid);
+int wlk_qwen_session_state(wlk_qwen* q, int32_t sid, int32_t* pending_frames, int64_t* emitted_steps);
+/* forward_chunk (causal.py:713-782) for n sessions at once.  mels_host holds the new mel frames of all sessions
+ * back to back ([frames][n_mels] fp32, session i = rows frame_offsets[i] .. frame_offsets[i+1]); every complete
+ * block (or chunk) is encoded; the newly emitted rows [steps][out_dim] of session i land in
+ * out_host[out_row_offsets[i] .. out_row_offsets[i+1]).                                                       */
+int wlk_qwen_forward_chunk(wlk_qwen* q, const int32_t* sids, int n, const float* mels_host, const int32_t* frame_offsets,
+                           float* out_host, int64_t out_capacity_rows, int32_t* out_row_offsets);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,12 @@ class wlk_dims(C.Structure):
         "n_vocab", "n_text_ctx", "n_text_state", "n_text_head", "n_text_layer")]
 
 
+class wlk_qwen_dims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_mels", "conv_channels", "d_model", "n_head", "n_layer", "ffn_dim", "out_dim", "max_positions",
+        "chunk_frames", "block_frames", "left_context_steps", "block_bidirectional", "conv_out_bias")]
+
+
 class wlk_config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "device", "precision", "max_sessions", "max_batch", "gemm_backend", "attn_backend",
@@ -55,6 +61,16 @@ SIGNATURES = {
     "wlk_session_clear_audio": (C.c_int, [_vp, C.c_int32]),
     "wlk_session_audio_len": (C.c_int, [_vp, C.c_int32, _i64p]),
     "wlk_session_reset_decoder": (C.c_int, [_vp, C.c_int32]),
+    "wlk_qwen_create": (C.c_int, [_vp, _vp, _vp]),
+    "wlk_qwen_destroy": (C.c_int, [_vp]),
+    "wlk_qwen_load_tensor": (C.c_int, [_vp, C.c_char_p, _vp, _vp, C.c_int]),
+    "wlk_qwen_finalize_weights": (C.c_int, [_vp]),
+    "wlk_qwen_memory": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "wlk_qwen_session_open": (C.c_int, [_vp, _vp]),
+    "wlk_qwen_session_close": (C.c_int, [_vp, C.c_int32]),
+    "wlk_qwen_session_reset": (C.c_int, [_vp, C.c_int32]),
+    "wlk_qwen_session_state": (C.c_int, [_vp, C.c_int32, _vp, _vp]),
+    "wlk_qwen_forward_chunk": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int64, _vp]),
     "wlk_session_fork": (C.c_int, [_vp, C.c_int32, _vp]),
     "wlk_sessions_gather_decoder": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "wlk_encode": (C.c_int, [_vp, _vp, C.c_int, _vp]),
