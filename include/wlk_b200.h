@@ -207,6 +207,11 @@ int wlk_qwen_session_state(wlk_qwen* q, int32_t sid, int32_t* pending_frames, in
 int wlk_qwen_forward_chunk(wlk_qwen* q, const int32_t* sids, int n, const float* mels_host, const int32_t* frame_offsets,
                            float* out_host, int64_t out_capacity_rows, int32_t* out_row_offsets);
 
+/* flush_pending (causal.py:687-711), end of stream: the buffered whole 8-frame chunks of each session are encoded as
+ * one piece (whatever the block size), a sub-chunk remainder is dropped.                                          */
+int wlk_qwen_flush_pending(wlk_qwen* q, const int32_t* sids, int n, float* out_host, int64_t out_capacity_rows,
+                           int32_t* out_row_offsets);
+
 #ifdef __cplusplus
 }
 #endif

@@ -118,6 +118,13 @@ def main():
                     idx = np.arange(0, flat.shape[0], max(1, flat.shape[0] // 509), dtype=np.int64)
                     rec[f"idx{i}"], rec[f"val{i}"] = idx, flat[idx].astype(np.float32)
                     rec[f"rowsum{i}"] = h.astype(np.float64).sum(axis=1).astype(np.float32)
+            hidden, state = enc.flush_pending(state)                      # end of stream (causal.py:687-711)
+            h = hidden[0].numpy()
+            rec["flush_steps"] = np.asarray(h.shape[0], np.int64)
+            rec["flush_emitted"] = np.asarray(state.emitted_steps, np.int64)
+            if h.size:
+                rec["flush_rowsum"] = h.astype(np.float64).sum(axis=1).astype(np.float32)
+                rec["flush_first_row"] = h[0].astype(np.float32)
         np.savez_compressed(os.path.join(out_dir, f"qwen_{name}.npz"), **rec)
         print(name, "emitted", state.emitted_steps, "pending", state.pending_frames, "std", float(np.std(h)))
 

@@ -2,6 +2,7 @@
 
 Restates reference third_party/qwen3-asr-causal/src/qwen3_asr_causal/causal.py in plain torch CPU ops:
   forward_chunk        :713-782   buffering to whole blocks, one _encode_ready_mels per block
+  flush_pending        :687-711   end of stream: the buffered whole 8-frame chunks, as one piece
   _encode_ready_mels   :642-681   conv blocks -> L layers with per-layer K/V cache -> ln_post/proj1/GELU/proj2
   _conv_one_block      :230-248   three 3x3 stride-2 convs + GELU on one 8-frame chunk, linear, + sinusoid(position)
   _position_embedding  :204-228   table rows, or the closed form beyond the table
@@ -148,4 +149,16 @@ class QwenTowerOracle:
                 out.append(torch.cat(rows, dim=0).numpy())
             else:
                 out.append(self._encode_ready(s, buf[:ready]).numpy())
+        return out
+
+    @torch.no_grad()
+    def flush_pending(self, sids: Sequence[int]) -> List[np.ndarray]:
+        """causal.py:687-711: encode the buffered whole conv chunks (< one block) as one piece, drop the rest."""
+        D = self.dims
+        out = []
+        for sid in sids:
+            s = self._s[sid]
+            ready = (s["buf"].shape[0] // D.chunk_frames) * D.chunk_frames
+            buf, s["buf"] = s["buf"], torch.zeros(0, D.n_mels)
+            out.append(self._encode_ready(s, buf[:ready]).numpy() if ready else np.zeros((0, D.out_dim), np.float32))
         return out

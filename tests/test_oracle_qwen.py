@@ -35,6 +35,12 @@ def check_stream(engine, g, mels, sched, tol):
             flat = h.reshape(-1)
             worst = max(worst, float(np.abs(flat[g[f"idx{i}"]] - g[f"val{i}"]).max()))
             worst = max(worst, float(np.abs(h.astype(np.float64).sum(axis=1) - g[f"rowsum{i}"]).max()) / h.shape[1] ** 0.5)
+    h = engine.flush_pending([sid])[0]                                   # end of stream
+    assert h.shape[0] == int(g["flush_steps"]) and engine.emitted_steps(sid) == int(g["flush_emitted"])
+    assert engine.pending_frames(sid) == 0
+    if h.size:
+        worst = max(worst, float(np.abs(h[0] - g["flush_first_row"]).max()))
+        worst = max(worst, float(np.abs(h.astype(np.float64).sum(axis=1) - g["flush_rowsum"]).max()) / h.shape[1] ** 0.5)
     engine.close_session(sid)
     assert worst < tol, worst
     return worst

@@ -1,0 +1,43 @@
+"""Build container only: the Qwen3 seam.  The reference's QwenAudioCausalKVEncoder and the drop-in built FROM it
+(weights taken from its tower's state_dict, geometry read off its modules) are driven with the same ragged chunk
+schedule; hidden states and the state fields callers read must agree.  The CPU oracle stands behind the engine API."""
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.reference
+
+
+@pytest.mark.parametrize("name", ["qnano", "qnano-chunk"])
+def test_drop_in_encoder_equals_reference(name):
+    sys.path.insert(0, "/root/reference/third_party/qwen3-asr-causal/src")
+    from oracle.make_golden_qwen import SCHEDULE, mel_stream, reference_encoder
+    from oracle.qwen_oracle import QwenTowerOracle
+    from whisperlivekit_b200.qwen_dims import QWEN_DIMS, synthetic_tower_state_dict
+    from whisperlivekit_b200.qwen_plugin import B200QwenAudioCausalKVEncoder
+
+    dims = QWEN_DIMS[name]
+    ref = reference_encoder(dims, synthetic_tower_state_dict(dims, seed=23))
+    mine = B200QwenAudioCausalKVEncoder.from_reference(ref, engine_factory=lambda d, sd: QwenTowerOracle(d, sd))
+    assert mine.dims == dims                                              # geometry recovered from the modules
+    mels = torch.from_numpy(mel_stream(sum(SCHEDULE), dims.n_mels, seed=4))
+    sr, sm = ref.init_state(), mine.init_state()
+    a = 0
+    with torch.no_grad():
+        for n in SCHEDULE:
+            hr, sr = ref.forward_chunk(mels[None, a: a + n], sr)
+            hm, sm = mine.forward_chunk(mels[None, a: a + n], sm)
+            a += n
+            assert hm.shape == hr.shape
+            if hr.numel():
+                assert float((hm - hr).abs().max()) < 2e-5
+            for f in ("frames_seen", "emitted_steps", "pending_frames", "last_input_frames", "last_recomputed_frames"):
+                assert getattr(sm, f) == getattr(sr, f), f
+        hr, sr = ref.flush_pending(sr)
+        hm, sm = mine.flush_pending(sm)
+        assert hm.shape == hr.shape and (not hr.numel() or float((hm - hr).abs().max()) < 2e-5)
+        assert sm.emitted_steps == sr.emitted_steps and sm.pending_frames == 0
+    assert mine.right_context_frames == ref.right_context_frames
+    assert mine.output_steps_for_mel_frames(195) == ref.output_steps_for_mel_frames(195)

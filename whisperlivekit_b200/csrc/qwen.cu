@@ -507,13 +507,15 @@ void run_round_typed(wlk_qwen* q, int n_jobs, int R, const QJob* jobs_dev, void*
     CUDA_CHECK(cudaGetLastError());
 }
 
+// flush = false: forward_chunk (causal.py:713-782).  flush = true: flush_pending (causal.py:687-711) -- no new frames,
+// the buffered whole 8-frame chunks are encoded as one piece regardless of the block size, the remainder is dropped.
 void forward_chunk(wlk_qwen* q, const int32_t* sids, int n, const float* mels, const int32_t* frame_off, float* out,
-                   int64_t cap_rows, int32_t* out_row_off) {
+                   int64_t cap_rows, int32_t* out_row_off, bool flush) {
     const wlk_qwen_dims& D = q->dims;
     WLK_CHECK(q->finalized, "weights not finalized");
     WLK_CHECK(n >= 1 && n <= q->cfg.max_batch, "batch %d outside [1, %d]", n, q->cfg.max_batch);
-    const int consume = D.block_frames > 0 ? D.block_frames : 8;
-    const int steps_cap = D.block_frames > 0 ? D.block_frames / 8 : Q_STEPS_CAP;
+    const int consume = (D.block_frames > 0 && !flush) ? D.block_frames : 8;
+    const int steps_cap = (D.block_frames > 0 && !flush) ? D.block_frames / 8 : Q_STEPS_CAP;
     // append, split off what is ready (reference forward_chunk: causal.py:742-752)
     std::vector<std::vector<float>> ready(n);
     std::vector<int> done_steps(n, 0), total_steps(n, 0);
@@ -521,15 +523,18 @@ void forward_chunk(wlk_qwen* q, const int32_t* sids, int n, const float* mels, c
     for (int i = 0; i < n; ++i) {
         QSession& s = qsession(q, sids[i]);
         for (int j = 0; j < i; ++j) WLK_CHECK(sids[j] != sids[i], "session %d appears twice in the batch", sids[i]);
-        const int nf = frame_off[i + 1] - frame_off[i];
-        WLK_CHECK(nf >= 0, "negative frame count");
-        s.pending.insert(s.pending.end(), mels + (size_t)frame_off[i] * D.n_mels, mels + (size_t)frame_off[i + 1] * D.n_mels);
+        if (!flush) {
+            const int nf = frame_off[i + 1] - frame_off[i];
+            WLK_CHECK(nf >= 0, "negative frame count");
+            s.pending.insert(s.pending.end(), mels + (size_t)frame_off[i] * D.n_mels, mels + (size_t)frame_off[i + 1] * D.n_mels);
+        }
         const int have = (int)(s.pending.size() / D.n_mels);
         const int take = have / consume * consume;
-        if (D.block_frames == 0 && D.block_bidirectional)
+        if ((D.block_frames == 0 || flush) && D.block_bidirectional)
             WLK_CHECK(take / 8 <= Q_STEPS_CAP, "bidirectional attention over %d steps in one call exceeds %d", take / 8, Q_STEPS_CAP);
         ready[i].assign(s.pending.begin(), s.pending.begin() + (size_t)take * D.n_mels);
         s.pending.erase(s.pending.begin(), s.pending.begin() + (size_t)take * D.n_mels);
+        if (flush) s.pending.clear();                     // a sub-chunk remainder carries no decodable content (causal.py:697-705)
         total_steps[i] = take / 8;
         out_row_off[i] = (int32_t)rows_total;
         rows_total += total_steps[i];
@@ -541,7 +546,7 @@ void forward_chunk(wlk_qwen* q, const int32_t* sids, int n, const float* mels, c
         std::vector<int> who;
         for (int i = 0; i < n; ++i) if (done_steps[i] < total_steps[i]) who.push_back(i);
         if (who.empty()) break;
-        const int nj = (int)who.size();
+        int nj = (int)who.size();
         // carve the staging block
         size_t off = 0;
         auto carve = [&](size_t bytes) { size_t o = (off + 255) / 256 * 256; off = o + bytes; WLK_CHECK(off <= q->stg_bytes, "staging overflow"); return o; };
@@ -549,7 +554,12 @@ void forward_chunk(wlk_qwen* q, const int32_t* sids, int n, const float* mels, c
         int R = 0;
         std::vector<int> steps(nj);
         for (int k = 0; k < nj; ++k) { steps[k] = std::min(steps_cap, total_steps[who[k]] - done_steps[who[k]]); R += steps[k]; }
-        WLK_CHECK(R <= q->max_rows, "round of %d steps exceeds the workspace (%d)", R, q->max_rows);
+        if (R > q->max_rows) {                            // a flush may carry up to block-1 frames per session: trim the round
+            int acc = 0, keep = 0;
+            while (keep < nj && acc + steps[keep] <= q->max_rows) acc += steps[keep++];
+            WLK_CHECK(keep >= 1, "round of %d steps exceeds the workspace (%d)", steps[0], q->max_rows);
+            who.resize(keep); steps.resize(keep); R = acc; nj = keep;
+        }
         const size_t o_slot = carve((size_t)R * 4), o_ring = carve((size_t)R * 4), o_abs = carve((size_t)R * 4);
         QJob* jobs = reinterpret_cast<QJob*>(q->stg_h + o_jobs);
         void** kvp = reinterpret_cast<void**>(q->stg_h + o_kv);
@@ -687,7 +697,16 @@ int wlk_qwen_forward_chunk(wlk_qwen* q, const int32_t* sids, int n, const float*
     QLOCK(q);
     WLK_CHECK(sids && frame_offsets && out_row_offsets && (mels_host || frame_offsets[n] == frame_offsets[0]), "null argument");
     WLK_CHECK(out_host || out_capacity_rows == 0, "null output buffer");
-    forward_chunk(q, sids, n, mels_host, frame_offsets, out_host, out_capacity_rows, out_row_offsets);
+    forward_chunk(q, sids, n, mels_host, frame_offsets, out_host, out_capacity_rows, out_row_offsets, false);
+    WLK_API_END
+}
+int wlk_qwen_flush_pending(wlk_qwen* q, const int32_t* sids, int n, float* out_host, int64_t out_capacity_rows,
+                           int32_t* out_row_offsets) {
+    WLK_API_BEGIN
+    QLOCK(q);
+    WLK_CHECK(sids && out_row_offsets, "null argument");
+    WLK_CHECK(out_host || out_capacity_rows == 0, "null output buffer");
+    forward_chunk(q, sids, n, nullptr, nullptr, out_host, out_capacity_rows, out_row_offsets, true);
     WLK_API_END
 }
 int wlk_qwen_memory(wlk_qwen* q, size_t* weights, size_t* sessions, size_t* workspace) {

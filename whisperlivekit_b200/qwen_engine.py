@@ -91,6 +91,17 @@ class QwenTowerEngine:
         L.check(self.lib.wlk_qwen_forward_chunk(self.h, _ptr(ids), n, _ptr(flat), _ptr(offs), _ptr(out), cap, _ptr(rows)))
         return [out[rows[i]: rows[i + 1]].copy() for i in range(n)]
 
+    def flush_pending(self, sids: Sequence[int]) -> List[np.ndarray]:
+        """End of stream (causal.py:687-711): encode the buffered whole chunks, drop the sub-chunk remainder."""
+        n = len(sids)
+        D = self.dims
+        cap = int(sum(self.pending_frames(s) // D.chunk_frames for s in sids))
+        out = np.zeros((max(cap, 1), D.out_dim), np.float32)
+        rows = np.zeros(n + 1, np.int32)
+        ids = np.asarray(list(sids), np.int32)
+        L.check(self.lib.wlk_qwen_flush_pending(self.h, _ptr(ids), n, _ptr(out), cap, _ptr(rows)))
+        return [out[rows[i]: rows[i + 1]].copy() for i in range(n)]
+
     def close(self) -> None:
         if not self._closed:
             self._closed = True
