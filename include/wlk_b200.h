@@ -73,6 +73,10 @@ int wlk_engine_memory(wlk_engine* e, size_t* weights, size_t* sessions, size_t* 
 int wlk_session_open(wlk_engine* e, int32_t* sid);
 int wlk_session_close(wlk_engine* e, int32_t sid);
 int wlk_session_append_audio(wlk_engine* e, int32_t sid, const float* pcm_host, int64_t n);
+/* ingest step before the path: the wire format is s16le PCM, which the reference
+ * converts on the host (audio_processor.py:416-418: int16 / 32768.0); here half the bytes cross PCIe and the
+ * conversion runs on the device straight into the session's ring.                                             */
+int wlk_session_append_pcm16(wlk_engine* e, int32_t sid, const int16_t* pcm_host, int64_t n);
 int wlk_session_drop_audio(wlk_engine* e, int32_t sid, int64_t n_front_samples);
 int wlk_session_clear_audio(wlk_engine* e, int32_t sid);
 int wlk_session_audio_len(wlk_engine* e, int32_t sid, int64_t* n);

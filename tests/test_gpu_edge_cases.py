@@ -124,3 +124,18 @@ def test_error_contract(pair):
         eng.open_session()
     for x in sids:
         eng.close_session(x)
+
+
+def test_pcm16_ingest_equals_host_conversion(pair):
+    """wlk_session_append_pcm16 == the reference's host conversion (int16 / 32768.0) followed by append_audio: same
+    mel, bit for bit."""
+    eng, orc, g, dims = pair
+    pcm = (np.clip(synthetic_audio(2.0, seed=21), -1, 1) * 32767).astype(np.int16)
+    a, b = eng.open_session(), eng.open_session()
+    eng.append_pcm16(a, pcm[:12000].tobytes())
+    eng.append_pcm16(a, pcm[12000:])
+    eng.append_audio(b, pcm.astype(np.float32) / 32768.0)
+    assert eng.audio_len(a) == eng.audio_len(b) == len(pcm)
+    assert eng.encode([a, b]) == [100, 100]
+    assert np.array_equal(eng.read_mel(a), eng.read_mel(b))
+    eng.close_session(a); eng.close_session(b)

@@ -135,15 +135,17 @@ def test_rolling_window_drop_audio_matches_oracle():
     eng.close_session(se)
 
 
-def test_large_v3_fp32_logits_match_oracle():
-    """True large-v3 geometry, seeded weights: CUDA fp32 mode vs the CPU oracle, 1e-3 on logits."""
+@pytest.mark.parametrize("model", ["large-v3", "base.en", "large-v3-turbo"])
+def test_true_geometry_fp32_logits_match_oracle(model):
+    """True model geometries of BASELINE.json's configs (large-v3; base.en = config 2; the 4-decoder-layer turbo),
+    seeded weights: CUDA fp32 mode vs the CPU oracle, 1e-3 on logits."""
     from oracle import whisper_oracle as wo
     from whisperlivekit_b200.engine import WhisperEngine
     for k in list(_ENGINES):
         _ENGINES.pop(k).close()
-    dims = DIMS["large-v3"]
+    dims = DIMS[model]
     sd = synthetic_state_dict(dims, seed=3)
-    heads = ALIGNMENT_HEADS["large-v3"]
+    heads = ALIGNMENT_HEADS[model]
     audio = synthetic_audio(5.0, seed=9)
     eng = WhisperEngine(dims, sd, heads, precision="fp32", max_sessions=1, max_batch=1)
     orc = wo.OracleEngine(dims, sd, heads)

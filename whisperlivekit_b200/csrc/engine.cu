@@ -1116,6 +1116,20 @@ int wlk_session_append_audio(wlk_engine* e, int32_t sid, const float* pcm, int64
     s.audio_len += n;
     WLK_API_END
 }
+int wlk_session_append_pcm16(wlk_engine* e, int32_t sid, const int16_t* pcm, int64_t n) {
+    WLK_API_BEGIN
+    LOCK(e);
+    Session& s = get_root_session(e, sid, "the audio ring");
+    WLK_CHECK(n >= 0 && (n == 0 || pcm), "bad audio chunk");
+    WLK_CHECK(s.audio_len + n <= AUDIO_CAP, "audio buffer overflow: %lld + %lld > %d samples", (long long)s.audio_len, (long long)n, AUDIO_CAP);
+    if (n) {
+        // the raw bytes land in the (idle between calls) audio scratch, the conversion writes the ring in place
+        CUDA_CHECK(cudaMemcpyAsync(e->audio_scratch, pcm, (size_t)n * 2, cudaMemcpyHostToDevice, e->st));
+        pcm16_to_f32(reinterpret_cast<const int16_t*>(e->audio_scratch), s.audio + s.audio_len, n, e->st);
+    }
+    s.audio_len += n;
+    WLK_API_END
+}
 int wlk_session_drop_audio(wlk_engine* e, int32_t sid, int64_t n) {
     WLK_API_BEGIN
     LOCK(e);

@@ -229,6 +229,18 @@ void convert_f32_to(const float* src, void* dst, int dst_type, int64_t n, cudaSt
     else cvt_from_f32_kernel<bf16><<<grid, 256, 0, st>>>(src, (bf16*)dst, n);
     CUDA_CHECK(cudaGetLastError());
 }
+// s16le PCM -> fp32 in [-1, 1): reference audio_processor.py:416-418 (np.int16 / 32768.0), exact in fp32
+__global__ void pcm16_to_f32_kernel(const int16_t* __restrict__ s, float* __restrict__ d, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        d[i] = (float)s[i] * (1.0f / 32768.0f);
+}
+void pcm16_to_f32(const int16_t* src, float* dst, int64_t n, cudaStream_t st) {
+    if (n <= 0) return;
+    int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    pcm16_to_f32_kernel<<<grid, 256, 0, st>>>(src, dst, n);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 void convert_to_f32(const void* src, int src_type, float* dst, int64_t n, cudaStream_t st) {
     int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
     if (grid < 1) grid = 1;

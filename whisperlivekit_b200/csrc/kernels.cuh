@@ -94,6 +94,7 @@ void dtw_batch(const void* jobs_dev, int n_jobs, int max_tokens, cudaStream_t st
 
 void convert_f32_to(const float* src, void* dst, int dst_type, int64_t n, cudaStream_t st);
 void convert_to_f32(const void* src, int src_type, float* dst, int64_t n, cudaStream_t st);
+void pcm16_to_f32(const int16_t* src_dev, float* dst_dev, int64_t n, cudaStream_t st);
 // conv weight [c_out, c_in, 3] -> [c_out, 3 * c_in] (tap-major) in the destination type
 void pack_conv_weight(const float* w, void* dst, int dst_type, int c_out, int c_in, cudaStream_t st);
 

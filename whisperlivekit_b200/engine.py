@@ -108,6 +108,11 @@ class WhisperEngine:
         a = np.ascontiguousarray(np.asarray(pcm, dtype=np.float32).reshape(-1))
         L.check(self.lib.wlk_session_append_audio(self.h, sid, _ptr(a), a.shape[0]))
 
+    def append_pcm16(self, sid: int, pcm) -> None:
+        """s16le samples (bytes or int16 array), converted to fp32 / 32768 on the device (audio_processor.py:416-418)."""
+        a = np.frombuffer(pcm, dtype=np.int16) if isinstance(pcm, (bytes, bytearray, memoryview)) else np.ascontiguousarray(pcm, np.int16)
+        L.check(self.lib.wlk_session_append_pcm16(self.h, sid, _ptr(a), a.shape[0]))
+
     def drop_audio(self, sid: int, n: int) -> None:
         L.check(self.lib.wlk_session_drop_audio(self.h, sid, int(n)))
 
