@@ -149,8 +149,6 @@ int wlk_read_align_attn(wlk_engine* e, int32_t sid, float* out, int64_t capacity
 int wlk_op_gemm(wlk_engine* e, int backend, const void* A, int a_type, int64_t lda,
                 const void* W, int w_type, int64_t ldw, const float* bias,
                 void* C, int c_type, int64_t ldc, int M, int N, int K, int gelu);
-int wlk_op_mel(wlk_engine* e, const float* audio_dev, int64_t n_samples, float* mel_out_dev /* [n_mels,3000] */,
-               int32_t* content_mel_len);
 int wlk_op_encoder_attention(wlk_engine* e, int backend, const void* qkv, int type, int batch, void* out);
 
 /* ---- word-timestamp kernels of the LocalAgreement path: native replacements of the reference's Triton

@@ -90,7 +90,6 @@ SIGNATURES = {
     "wlk_read_align_attn": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, _i32p, _i32p]),
     "wlk_op_gemm": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int64, _vp, C.c_int, C.c_int64, _vp,
                               _vp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int]),
-    "wlk_op_mel": (C.c_int, [_vp, _vp, C.c_int64, _vp, _i32p]),
     "wlk_op_encoder_attention": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp]),
     "wlk_op_median_filter": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int]),
     "wlk_op_dtw": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _i32p]),

@@ -1392,10 +1392,6 @@ int wlk_op_gemm(wlk_engine* e, int backend, const void* A, int a_type, int64_t l
     else gemm_simt(g, e->st);
     WLK_API_END
 }
-int wlk_op_mel(wlk_engine*, const float*, int64_t, float*, int32_t*) {
-    wlk::set_last_error("wlk_op_mel: use a session (append_audio + encode + read_mel)");
-    return 1;
-}
 int wlk_op_encoder_attention(wlk_engine* e, int backend, const void* qkv, int type, int batch, void* out) {
     WLK_API_BEGIN
     LOCK(e);
