@@ -209,6 +209,13 @@ int wlk_qwen_session_state(wlk_qwen* q, int32_t sid, int32_t* pending_frames, in
 int wlk_qwen_forward_chunk(wlk_qwen* q, const int32_t* sids, int n, const float* mels_host, const int32_t* frame_offsets,
                            float* out_host, int64_t out_capacity_rows, int32_t* out_row_offsets);
 
+/* StreamingMelExtractor.append (flush = 0) / .flush (flush = 1), reference features.py:86-110, for n sessions: the
+ * raw sample window of every stream stays on the device; the call featurizes the windows (Hugging Face
+ * WhisperFeatureExtractor semantics: reflect-padded 400-point STFT, hop 160, Slaney mel bank loaded as tensor
+ * "mel_filters" [n_mels][201], log10, clamp to the window's max - 8, (x + 4) / 4) and returns the newly determined
+ * frames [frames][n_mels] of session i in mel_out_host[frame_offsets_out[i] .. frame_offsets_out[i+1]).           */
+int wlk_qwen_append_audio(wlk_qwen* q, const int32_t* sids, int n, const float* pcm_host, const int64_t* sample_offsets,
+                          float* mel_out_host, int64_t out_capacity_frames, int32_t* frame_offsets_out, int32_t flush);
 /* flush_pending (causal.py:687-711), end of stream: the buffered whole 8-frame chunks of each session are encoded as
  * one piece (whatever the block size), a sub-chunk remainder is dropped.                                          */
 int wlk_qwen_flush_pending(wlk_qwen* q, const int32_t* sids, int n, float* out_host, int64_t out_capacity_rows,

@@ -32,6 +32,7 @@ REF = "/root/reference"
 def import_reference():
     if "soundfile" not in sys.modules:                      # only OpenaiApiASR needs it
         m = types.ModuleType("soundfile")
+        m.__spec__ = __import__("importlib.machinery").machinery.ModuleSpec("soundfile", loader=None)   # find_spec() must not choke on the stub
         m.read = m.write = m.info = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("stub"))
         sys.modules["soundfile"] = m
     if REF not in sys.path:

@@ -51,6 +51,26 @@ class QwenTowerOracle:
     def reset_session(self, sid: int) -> None:
         self._s[sid] = dict(buf=torch.zeros(0, self.dims.n_mels), caches=[None] * self.dims.n_layer, emitted=0)
 
+    # incremental log-mel front end behind the same method names as QwenTowerEngine (features.py:32-112)
+    def load_mel_filters(self, filters=None) -> None:
+        from whisperlivekit_b200.weights import mel_filterbank
+        self._filters = np.asarray(mel_filterbank(self.dims.n_mels) if filters is None else filters, np.float32)
+
+    def _mel(self, sid: int):
+        from oracle.qwen_mel_oracle import StreamingMelOracle
+        s = self._s[sid]
+        if "mel" not in s:
+            s["mel"] = StreamingMelOracle(self._filters)
+        return s["mel"]
+
+    def append_audio(self, sids, audios):
+        out = [self._mel(sid).append(a) for sid, a in zip(sids, audios)]
+        return [np.zeros((0, self.dims.n_mels), np.float32) if m is None else m for m in out]
+
+    def flush_audio(self, sids):
+        out = [self._mel(sid).flush() for sid in sids]
+        return [np.zeros((0, self.dims.n_mels), np.float32) if m is None else m for m in out]
+
     def pending_frames(self, sid: int) -> int:
         return int(self._s[sid]["buf"].shape[0])
 

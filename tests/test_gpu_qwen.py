@@ -106,3 +106,71 @@ def test_qwen_error_contract():
     with pytest.raises(WlkError, match="invalid session"):
         eng.forward_chunk([5], [mels[:8]])
     eng.close()
+
+
+def test_device_mel_front_end_matches_reference_extractor():
+    """wlk_qwen_append_audio (StreamingMelExtractor.append / flush on the device) against fixtures recorded from the
+    reference extractor over the Hugging Face featurizer: same frames per call, values within 2e-4 (fp32 DFT)."""
+    from test_oracle_qwen_mel import check_mel_stream, mel_case
+    from whisperlivekit_b200.qwen_engine import QwenTowerEngine
+    g, audio, sched = mel_case()
+    dims = QWEN_DIMS["qnano"]
+    eng = QwenTowerEngine(dims, None, precision="fp32", max_sessions=2, max_batch=2)
+    eng.load_mel_filters()
+    s = eng.open_session()
+    seen = [0]
+
+    def append(a):
+        m = eng.append_audio([s], [a])[0]
+        seen[0] += m.shape[0]
+        return m
+
+    def flush():
+        m = eng.flush_audio([s])[0]
+        seen[0] += m.shape[0]
+        return m
+
+    check_mel_stream(append, flush, lambda: seen[0], g, audio, sched, 2e-4)
+    eng.close()
+
+
+def test_audio_to_tower_end_to_end_batched():
+    """Raw audio of three streams, appended in different chunkings, through the device mel front end and the tower,
+    against the oracle chain (StreamingMelOracle -> QwenTowerOracle) stream by stream."""
+    from oracle.make_golden_qwen_mel import speechlike
+    from oracle.qwen_mel_oracle import StreamingMelOracle
+    from oracle.qwen_oracle import QwenTowerOracle
+    from whisperlivekit_b200.qwen_engine import QwenTowerEngine
+    from whisperlivekit_b200.weights import mel_filterbank
+    dims = QWEN_DIMS["qnano"]
+    sd = synthetic_tower_state_dict(dims, seed=11)
+    eng = QwenTowerEngine(dims, sd, precision="fp32", max_sessions=3, max_batch=3)
+    eng.load_mel_filters()
+    audio = [speechlike(16000 * 7, seed=40 + i) for i in range(3)]
+    chunk = [4000, 2560, 9000]
+    sids = [eng.open_session() for _ in range(3)]
+    orc = QwenTowerOracle(dims, sd)
+    osid = [orc.open_session() for _ in range(3)]
+    omel = [StreamingMelOracle(mel_filterbank(dims.n_mels)) for _ in range(3)]
+    pos = [0, 0, 0]
+    worst, rows = 0.0, 0
+    for call in range(12):
+        parts = []
+        for i in range(3):
+            parts.append(audio[i][pos[i]: pos[i] + chunk[i]])
+            pos[i] += chunk[i]
+        mels = eng.append_audio(sids, parts)
+        got = eng.forward_chunk(sids, mels)
+        for i in range(3):
+            m = omel[i].append(parts[i])
+            m = np.zeros((0, dims.n_mels), np.float32) if m is None else m
+            assert mels[i].shape == m.shape
+            if m.size:
+                assert np.abs(mels[i] - m).max() < 2e-4
+            ref = orc.forward_chunk([osid[i]], [m])[0]
+            assert got[i].shape == ref.shape
+            if ref.size:
+                worst = max(worst, float(np.abs(got[i] - ref).max()))
+                rows += ref.shape[0]
+    assert rows > 100 and worst < 2e-3, (rows, worst)
+    eng.close()

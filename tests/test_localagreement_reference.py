@@ -17,6 +17,7 @@ pytestmark = pytest.mark.reference
 def _import_reference():
     if "soundfile" not in sys.modules:
         m = types.ModuleType("soundfile")
+        m.__spec__ = __import__("importlib.machinery").machinery.ModuleSpec("soundfile", loader=None)   # find_spec() must not choke on the stub
         m.read = m.write = m.info = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("stub"))
         sys.modules["soundfile"] = m
     if "/root/reference" not in sys.path:

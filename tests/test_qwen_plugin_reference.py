@@ -41,3 +41,33 @@ def test_drop_in_encoder_equals_reference(name):
         assert sm.emitted_steps == sr.emitted_steps and sm.pending_frames == 0
     assert mine.right_context_frames == ref.right_context_frames
     assert mine.output_steps_for_mel_frames(195) == ref.output_steps_for_mel_frames(195)
+
+
+def test_drop_in_mel_extractor_equals_reference():
+    """StreamingMelExtractor (reference, over the real Hugging Face featurizer) vs the drop-in over the engine API
+    (CPU oracle behind it): same frames per append / flush, same values."""
+    sys.path.insert(0, "/root/reference/third_party/qwen3-asr-causal/src")
+    from transformers import WhisperFeatureExtractor
+    from qwen3_asr_causal.features import StreamingMelExtractor
+    from oracle.make_golden_qwen_mel import speechlike
+    from oracle.qwen_oracle import QwenTowerOracle
+    from whisperlivekit_b200.qwen_dims import QWEN_DIMS, synthetic_tower_state_dict
+    from whisperlivekit_b200.qwen_plugin import B200StreamingMelExtractor
+
+    dims = QWEN_DIMS["qnano"]
+    eng = QwenTowerOracle(dims, synthetic_tower_state_dict(dims, seed=1))
+    eng.load_mel_filters()
+    ref = StreamingMelExtractor(WhisperFeatureExtractor(feature_size=128))
+    mine = B200StreamingMelExtractor(eng, eng.open_session())
+    audio = speechlike(16000 * 4, seed=77)
+    a = 0
+    for n in (100, 150, 4000, 333, 4000, 0, 12000, 4001):
+        r, m = ref.append(audio[a: a + n]), mine.append(audio[a: a + n])
+        a += n
+        assert (r is None) == (m is None)
+        if r is not None:
+            assert tuple(r.shape) == tuple(m.shape) and float((r - m).abs().max()) < 5e-5
+        assert ref.emitted_frames == mine.emitted_frames
+    r, m = ref.flush(), mine.flush()
+    assert (r is None) == (m is None) and (r is None or float((r - m).abs().max()) < 5e-5)
+    assert ref.emitted_frames == mine.emitted_frames == a // 160

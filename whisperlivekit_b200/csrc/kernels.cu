@@ -85,7 +85,8 @@ mel_power_kernel(const MelJob* __restrict__ jobs, int n_mels, const float* __res
     auto sample = [&](int fr, int j) -> float {         // windowed sample j of frame fr
         int s = (f0 + fr) * HOP - HALF + j;             // torch.stft(center=True): reflect pad n_fft/2
         if (s < 0) s = -s;
-        const float x = (s < job.n) ? job.audio[s] : 0.f;   // right of the audio: the appended zeros
+        if (job.pad && s >= job.n) s = 2 * (job.n - 1) - s;  // streaming window: reflect at the right edge too
+        const float x = (s >= 0 && s < job.n) ? job.audio[s] : 0.f;   // right of the audio: the appended zeros
         return x * window[j];
     };
     for (int i = tid; i < FR * HALF; i += 224) {
@@ -175,6 +176,35 @@ void mel_forward(const MelJob* jobs_dev, int batch, int n_mels, const float* fil
     dim3 g2(64, batch);
     if (out_type == DT_F32) mel_finalize_kernel<float><<<g2, 256, 0, st>>>(jobs_dev, n_mels);
     else mel_finalize_kernel<bf16><<<g2, 256, 0, st>>>(jobs_dev, n_mels);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// Incremental front end of the Qwen3 streaming backend (reference third_party/qwen3-asr-causal/src/qwen3_asr_causal/
+// features.py:50-84): features of one sample WINDOW -- reflect padding at both edges (MelJob.pad = 1), clamp against
+// the window's own maximum -- of which frames [first, last) are emitted as fp32 [frames][n_mels].
+__global__ void __launch_bounds__(256)
+mel_window_finalize_kernel(const MelJob* __restrict__ jobs, const int2* __restrict__ ranges /* (first, last) */,
+                           const int64_t* __restrict__ out_off, float* __restrict__ out, int n_mels) {
+    __shared__ float red[8];
+    const MelJob job = jobs[blockIdx.y];
+    float m = -INFINITY;
+    const int n_ctas = (job.n_compute + MEL_FRAMES_PER_CTA - 1) / MEL_FRAMES_PER_CTA;
+    for (int i = threadIdx.x; i < n_ctas; i += 256) m = fmaxf(m, job.blockmax[i]);
+    const float thr = block_max_all<256>(m, red) - 8.0f;
+    const int2 r = ranges[blockIdx.y];
+    const int64_t total = (int64_t)(r.y - r.x) * n_mels;
+    float* o = out + out_off[blockIdx.y] * n_mels;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256)
+        o[i] = (fmaxf(job.raw[(int64_t)r.x * n_mels + i], thr) + 4.0f) * 0.25f;
+}
+void mel_window_forward(const MelJob* jobs_dev, const int2* ranges_dev, const int64_t* out_off_dev, float* out_dev, int batch,
+                        int n_mels, const float* filtT, const float* window, const float2* twiddle, const int2* filt_span,
+                        cudaStream_t st) {
+    dim3 g1(MEL_MAX_CTAS, batch);
+    mel_power_kernel<<<g1, 224, 0, st>>>(jobs_dev, n_mels, filtT, window, twiddle, filt_span);
+    CUDA_CHECK(cudaGetLastError());
+    dim3 g2(8, batch);
+    mel_window_finalize_kernel<<<g2, 256, 0, st>>>(jobs_dev, ranges_dev, out_off_dev, out_dev, n_mels);
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -29,6 +29,12 @@ struct MelJob {                 // one per session in the batch (device array)
 void mel_forward(const MelJob* jobs_dev, int batch, int n_mels, const float* filtT, const float* window,
                  const float2* twiddle, const int2* filt_span, int out_type, cudaStream_t st);
 
+// streaming-window variant (Qwen3 front end): MelJob.pad = 1, n_compute = n_total = window frames; emits frames
+// [ranges[i].x, ranges[i].y) of job i as fp32 [frames][n_mels] at row out_off[i] of `out`
+void mel_window_forward(const MelJob* jobs_dev, const int2* ranges_dev, const int64_t* out_off_dev, float* out_dev, int batch,
+                        int n_mels, const float* filtT, const float* window, const float2* twiddle, const int2* filt_span,
+                        cudaStream_t st);
+
 void mel_import(const float* mel_dev /*[n_mels,3000]*/, void* out /*[3002,n_mels]*/, int out_type, int n_mels, cudaStream_t st);
 
 void zero_rows(void* base, int type, int64_t row_elems, const int64_t* row_index_dev, int n_rows, cudaStream_t st);

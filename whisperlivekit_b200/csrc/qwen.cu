@@ -182,11 +182,17 @@ struct QLayerW {
     float *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr;
 };
 
+constexpr int QMEL_MAX_FRAMES = N_FRAMES;               // frames one featurized window may hold (30 s)
+constexpr int QMEL_AUDIO_CAP = QMEL_MAX_FRAMES * HOP + 2 * N_FFT;
+
 struct QSession {
     bool open = false;
     std::vector<float> pending;         // mel frames not yet consumed (host: the caller hands mels on the host)
     int64_t emitted = 0;                // encoder steps emitted so far == absolute position of the next step
     void* kv = nullptr;
+    // incremental log-mel front end (reference features.py:32-112): the sample window lives on the device
+    float* audio = nullptr; float* mel_raw = nullptr; float* mel_blockmax = nullptr;
+    int64_t buf_len = 0, buf_start_frame = 0, mel_emitted = 0, total_samples = 0;
 };
 
 }  // namespace
@@ -207,6 +213,9 @@ struct wlk_qwen {
     float *c1w = nullptr, *c1b = nullptr, *c2b = nullptr, *c3b = nullptr, *bout = nullptr, *pos_table = nullptr;
     void *W2c = nullptr, *W3c = nullptr, *Wout = nullptr, *Wp1 = nullptr, *Wp2 = nullptr;
     float *lnpw = nullptr, *lnpb = nullptr, *bp1 = nullptr, *bp2 = nullptr;
+    float *filtT = nullptr, *window = nullptr; float2* twiddle = nullptr; int2* filt_span = nullptr;   // mel front end
+    bool have_filters = false;
+    float* mel_out = nullptr; size_t mel_out_cap = 0; float* audio_scratch = nullptr;
     std::vector<QLayerW> L;
     std::set<std::string> loaded;
     bool finalized = false;
@@ -265,7 +274,26 @@ void load_tensor(wlk_qwen* q, const std::string& name, const float* host, const 
     const int64_t n = numel(shape, ndim);
     auto mat = [&](void* dst, int64_t rows, int64_t cols) { expect(name.c_str(), shape, ndim, {rows, cols}); put(q, host, n, dst, q->act); };
     auto vec = [&](float* dst, int64_t len) { expect(name.c_str(), shape, ndim, {len}); put(q, host, n, dst, DT_F32); };
-    if (name == "conv2d1.weight") { expect(name.c_str(), shape, ndim, {C, 1, 3, 3}); put(q, host, n, q->c1w, DT_F32); }
+    if (name == "mel_filters") {
+        // optional: only wlk_qwen_append_audio needs it.  [n_mels][201] (Slaney filterbank of the feature extractor)
+        expect(name.c_str(), shape, ndim, {D.n_mels, N_FREQ});
+        std::vector<float> t((size_t)n);
+        std::vector<int2> span(D.n_mels);
+        for (int m = 0; m < D.n_mels; ++m) {
+            int lo = N_FREQ, hi = 0;
+            for (int k = 0; k < N_FREQ; ++k) {
+                t[(size_t)k * D.n_mels + m] = host[(size_t)m * N_FREQ + k];
+                if (host[(size_t)m * N_FREQ + k] != 0.f) { if (k < lo) lo = k; hi = k + 1; }
+            }
+            if (lo >= hi) { lo = 0; hi = 0; }
+            span[m] = make_int2(lo, hi);
+        }
+        put(q, t.data(), n, q->filtT, DT_F32);
+        CUDA_CHECK(cudaMemcpyAsync(q->filt_span, span.data(), span.size() * 8, cudaMemcpyHostToDevice, q->st));
+        CUDA_CHECK(cudaStreamSynchronize(q->st));
+        q->have_filters = true;
+    }
+    else if (name == "conv2d1.weight") { expect(name.c_str(), shape, ndim, {C, 1, 3, 3}); put(q, host, n, q->c1w, DT_F32); }
     else if (name == "conv2d1.bias") vec(q->c1b, C);
     else if (name == "conv2d2.weight" || name == "conv2d3.weight") {
         // [Co][Ci][3][3] -> [Co][tap][Ci]: a tap's input channels are contiguous, like the im2col rows
@@ -410,7 +438,24 @@ void create(const wlk_qwen_dims* dims, const wlk_config* cfg, wlk_qwen** out) {
     q->xn = qalloc(q, R * d * es, ws); q->qb = qalloc(q, R * d * es, ws); q->att = qalloc(q, R * d * es, ws);
     q->hid = qalloc(q, R * (size_t)(ffn > d ? ffn : d) * es, ws);
     q->outbuf = (float*)qalloc(q, R * D.out_dim * 4, ws);
-    q->stg_bytes = R * 16 + (size_t)cfg->max_batch * (sizeof(QJob) + 16) + 4096;
+    q->filtT = (float*)qalloc(q, (size_t)N_FREQ * D.n_mels * 4, aw);
+    q->window = (float*)qalloc(q, N_FFT * 4, aw);
+    q->twiddle = (float2*)qalloc(q, N_FFT * 8, aw);
+    q->filt_span = (int2*)qalloc(q, (size_t)D.n_mels * 8, aw);
+    q->audio_scratch = (float*)qalloc(q, (size_t)QMEL_AUDIO_CAP * 4, ws);
+    {   // periodic Hann window and DFT twiddles exp(-2 pi i t / 400), evaluated in double
+        std::vector<float> win(N_FFT);
+        std::vector<float2> tw(N_FFT);
+        for (int t = 0; t < N_FFT; ++t) {
+            const double a = 2.0 * M_PI * t / N_FFT;
+            win[t] = (float)(0.5 - 0.5 * cos(a));
+            tw[t] = make_float2((float)cos(a), (float)-sin(a));
+        }
+        CUDA_CHECK(cudaMemcpyAsync(q->window, win.data(), N_FFT * 4, cudaMemcpyHostToDevice, q->st));
+        CUDA_CHECK(cudaMemcpyAsync(q->twiddle, tw.data(), N_FFT * 8, cudaMemcpyHostToDevice, q->st));
+        CUDA_CHECK(cudaStreamSynchronize(q->st));
+    }
+    q->stg_bytes = R * 16 + (size_t)cfg->max_batch * (sizeof(QJob) + sizeof(MelJob) + 64) + 4096;
     CUDA_CHECK(cudaMallocHost(&q->stg_h, q->stg_bytes));
     q->stg_d = (uint8_t*)qalloc(q, q->stg_bytes, ws);
     q->sess.resize(cfg->max_sessions);
@@ -419,7 +464,8 @@ void create(const wlk_qwen_dims* dims, const wlk_config* cfg, wlk_qwen** out) {
 
 void destroy(wlk_qwen* q) {
     cudaStreamSynchronize(q->st);
-    for (auto& s : q->sess) if (s.kv) cudaFree(s.kv);
+    for (auto& s : q->sess) { if (s.kv) cudaFree(s.kv); if (s.audio) cudaFree(s.audio); if (s.mel_raw) cudaFree(s.mel_raw); if (s.mel_blockmax) cudaFree(s.mel_blockmax); }
+    if (q->mel_out) cudaFree(q->mel_out);
     for (void* p : q->allocs) cudaFree(p);
     if (q->stage_f32) cudaFree(q->stage_f32);
     if (q->stg_h) cudaFreeHost(q->stg_h);
@@ -601,6 +647,100 @@ void forward_chunk(wlk_qwen* q, const int32_t* sids, int n, const float* mels, c
     }
 }
 
+// StreamingMelExtractor.append / .flush (reference features.py:86-110) for n sessions: the sample windows stay on the
+// device, one launch pair featurizes every session's window, the newly determined frames come back [frames][n_mels].
+void append_audio(wlk_qwen* q, const int32_t* sids, int n, const float* pcm, const int64_t* sample_off, float* out,
+                  int64_t cap_frames, int32_t* frame_off, bool flush) {
+    const wlk_qwen_dims& D = q->dims;
+    WLK_CHECK(q->have_filters, "load the \"mel_filters\" tensor [n_mels][201] before appending audio");
+    WLK_CHECK(n >= 1 && n <= q->cfg.max_batch, "batch %d outside [1, %d]", n, q->cfg.max_batch);
+    struct Plan { int first, last, frames; };
+    std::vector<Plan> plan(n, Plan{0, 0, 0});
+    std::vector<int> who;
+    int64_t rows = 0;
+    for (int i = 0; i < n; ++i) {
+        QSession& s = qsession(q, sids[i]);
+        for (int j = 0; j < i; ++j) WLK_CHECK(sids[j] != sids[i], "session %d appears twice in the batch", sids[i]);
+        if (!s.audio) {
+            CUDA_CHECK(cudaMalloc(&s.audio, (size_t)QMEL_AUDIO_CAP * 4));
+            CUDA_CHECK(cudaMalloc(&s.mel_raw, (size_t)(QMEL_MAX_FRAMES + 2) * D.n_mels * 4));
+            CUDA_CHECK(cudaMalloc(&s.mel_blockmax, (size_t)MEL_MAX_CTAS * 4));
+            q->bytes_sessions += (size_t)QMEL_AUDIO_CAP * 4 + (size_t)(QMEL_MAX_FRAMES + 2) * D.n_mels * 4 + MEL_MAX_CTAS * 4;
+        }
+        int64_t upto;
+        if (!flush) {
+            const int64_t ns = sample_off[i + 1] - sample_off[i];
+            WLK_CHECK(ns >= 0, "negative sample count");
+            WLK_CHECK(s.buf_len + ns <= QMEL_AUDIO_CAP - 2 * N_FFT, "audio window overflow: append at most %d s at a time", QMEL_MAX_FRAMES / 100);
+            if (ns) CUDA_CHECK(cudaMemcpyAsync(s.audio + s.buf_len, pcm + sample_off[i], (size_t)ns * 4, cudaMemcpyHostToDevice, q->st));
+            s.buf_len += ns; s.total_samples += ns;
+            frame_off[i] = (int32_t)rows;
+            if (s.total_samples < N_FFT / 2 + 1) continue;                               // features.py:93-94
+            upto = std::min((s.total_samples - N_FFT / 2) / HOP + 1, s.total_samples / HOP);   // :95-96
+        } else {
+            frame_off[i] = (int32_t)rows;
+            upto = s.total_samples / HOP;                                                // :103
+            if (upto <= s.mel_emitted) continue;
+            if (s.buf_len < N_FFT + 1) {                                                 // :106-108 zero-pad a short tail
+                CUDA_CHECK(cudaMemsetAsync(s.audio + s.buf_len, 0, (size_t)(N_FFT + 1 - s.buf_len) * 4, q->st));
+                s.buf_len = N_FFT + 1;
+            }
+        }
+        if (upto <= s.mel_emitted) continue;                                             // _emit, features.py:62-84
+        int64_t first = s.mel_emitted - s.buf_start_frame, last = upto - s.buf_start_frame;
+        const int64_t frames = s.buf_len / HOP;
+        if (frames < last) { last = frames; upto = s.buf_start_frame + last; if (upto <= s.mel_emitted) continue; }
+        WLK_CHECK(frames <= QMEL_MAX_FRAMES, "audio window of %lld frames exceeds %d", (long long)frames, QMEL_MAX_FRAMES);
+        plan[i] = Plan{(int)first, (int)last, (int)frames};
+        who.push_back(i);
+        rows += last - first;
+        s.mel_emitted = upto;
+    }
+    frame_off[n] = (int32_t)rows;
+    WLK_CHECK(rows <= cap_frames, "output buffer too small: %lld frames needed, %lld given", (long long)rows, (long long)cap_frames);
+    if (who.empty()) { CUDA_CHECK(cudaStreamSynchronize(q->st)); return; }
+    const int nj = (int)who.size();
+    if ((size_t)rows * D.n_mels > q->mel_out_cap) {
+        if (q->mel_out) { CUDA_CHECK(cudaStreamSynchronize(q->st)); cudaFree(q->mel_out); q->mel_out = nullptr; }
+        q->mel_out_cap = (size_t)rows * D.n_mels * 2;
+        CUDA_CHECK(cudaMalloc(&q->mel_out, q->mel_out_cap * 4));
+    }
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = (off + 255) / 256 * 256; off = o + bytes; WLK_CHECK(off <= q->stg_bytes, "staging overflow"); return o; };
+    const size_t o_jobs = carve(nj * sizeof(MelJob)), o_rng = carve(nj * sizeof(int2)), o_off = carve(nj * sizeof(int64_t));
+    MelJob* mj = reinterpret_cast<MelJob*>(q->stg_h + o_jobs);
+    int2* rng = reinterpret_cast<int2*>(q->stg_h + o_rng);
+    int64_t* ooff = reinterpret_cast<int64_t*>(q->stg_h + o_off);
+    for (int k = 0; k < nj; ++k) {
+        const int i = who[k];
+        QSession& s = q->sess[sids[i]];
+        mj[k] = MelJob{s.audio, s.mel_raw, s.mel_blockmax, nullptr, (int32_t)s.buf_len, plan[i].frames, plan[i].frames, 1};
+        rng[k] = make_int2(plan[i].first, plan[i].last);
+        ooff[k] = frame_off[i];
+    }
+    CUDA_CHECK(cudaMemcpyAsync(q->stg_d, q->stg_h, off, cudaMemcpyHostToDevice, q->st));
+    mel_window_forward(reinterpret_cast<const MelJob*>(q->stg_d + o_jobs), reinterpret_cast<const int2*>(q->stg_d + o_rng),
+                       reinterpret_cast<const int64_t*>(q->stg_d + o_off), q->mel_out, nj, D.n_mels, q->filtT, q->window,
+                       q->twiddle, q->filt_span, q->st);
+    CUDA_CHECK(cudaMemcpyAsync(out, q->mel_out, (size_t)rows * D.n_mels * 4, cudaMemcpyDeviceToHost, q->st));
+    // drop the samples no longer needed: keep MARGIN (8) frames of history before the next frame to emit (features.py:77-83)
+    for (int k = 0; k < nj; ++k) {
+        QSession& s = q->sess[sids[who[k]]];
+        const int64_t keep_from = std::max(s.buf_start_frame, s.mel_emitted - 8);
+        const int64_t cut = (keep_from - s.buf_start_frame) * HOP;
+        if (cut > 0) {
+            const int64_t keep = s.buf_len - cut;
+            if (keep > 0) {
+                CUDA_CHECK(cudaMemcpyAsync(q->audio_scratch, s.audio + cut, (size_t)keep * 4, cudaMemcpyDeviceToDevice, q->st));
+                CUDA_CHECK(cudaMemcpyAsync(s.audio, q->audio_scratch, (size_t)keep * 4, cudaMemcpyDeviceToDevice, q->st));
+            }
+            s.buf_len = keep > 0 ? keep : 0;
+            s.buf_start_frame = keep_from;
+        }
+    }
+    CUDA_CHECK(cudaStreamSynchronize(q->st));            // pcm / out belong to the caller; the staging block is reused
+}
+
 }  // namespace
 
 #define WLK_API_BEGIN try {
@@ -673,6 +813,10 @@ int wlk_qwen_session_close(wlk_qwen* q, int32_t sid) {
     CUDA_CHECK(cudaStreamSynchronize(q->st));
     cudaFree(s.kv);
     q->bytes_sessions -= (size_t)q->dims.n_layer * 2 * q->dims.n_head * q->ring * 64 * q->es();
+    if (s.audio) {
+        cudaFree(s.audio); cudaFree(s.mel_raw); cudaFree(s.mel_blockmax);
+        q->bytes_sessions -= (size_t)QMEL_AUDIO_CAP * 4 + (size_t)(QMEL_MAX_FRAMES + 2) * q->dims.n_mels * 4 + MEL_MAX_CTAS * 4;
+    }
     s = QSession{};
     WLK_API_END
 }
@@ -681,6 +825,7 @@ int wlk_qwen_session_reset(wlk_qwen* q, int32_t sid) {
     QLOCK(q);
     QSession& s = qsession(q, sid);
     s.emitted = 0; s.pending.clear();
+    s.buf_len = s.buf_start_frame = s.mel_emitted = s.total_samples = 0;       // StreamingMelExtractor.reset, features.py:112
     WLK_API_END
 }
 int wlk_qwen_session_state(wlk_qwen* q, int32_t sid, int32_t* pending_frames, int64_t* emitted_steps) {
@@ -707,6 +852,16 @@ int wlk_qwen_flush_pending(wlk_qwen* q, const int32_t* sids, int n, float* out_h
     WLK_CHECK(sids && out_row_offsets, "null argument");
     WLK_CHECK(out_host || out_capacity_rows == 0, "null output buffer");
     forward_chunk(q, sids, n, nullptr, nullptr, out_host, out_capacity_rows, out_row_offsets, true);
+    WLK_API_END
+}
+int wlk_qwen_append_audio(wlk_qwen* q, const int32_t* sids, int n, const float* pcm_host, const int64_t* sample_offsets,
+                          float* mel_out_host, int64_t out_capacity_frames, int32_t* frame_offsets_out, int32_t flush) {
+    WLK_API_BEGIN
+    QLOCK(q);
+    WLK_CHECK(sids && frame_offsets_out && (flush || sample_offsets), "null argument");
+    WLK_CHECK(flush || pcm_host || sample_offsets[n] == sample_offsets[0], "null audio");
+    WLK_CHECK(mel_out_host || out_capacity_frames == 0, "null output buffer");
+    append_audio(q, sids, n, pcm_host, sample_offsets, mel_out_host, out_capacity_frames, frame_offsets_out, flush != 0);
     WLK_API_END
 }
 int wlk_qwen_memory(wlk_qwen* q, size_t* weights, size_t* sessions, size_t* workspace) {

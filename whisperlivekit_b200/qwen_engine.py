@@ -91,6 +91,35 @@ class QwenTowerEngine:
         L.check(self.lib.wlk_qwen_forward_chunk(self.h, _ptr(ids), n, _ptr(flat), _ptr(offs), _ptr(out), cap, _ptr(rows)))
         return [out[rows[i]: rows[i + 1]].copy() for i in range(n)]
 
+    # -- incremental log-mel front end (StreamingMelExtractor, features.py:32-112) on the device -------------
+    def load_mel_filters(self, filters: Optional[np.ndarray] = None) -> None:
+        from .weights import mel_filterbank
+        a = np.ascontiguousarray(mel_filterbank(self.dims.n_mels) if filters is None else filters, np.float32)
+        shape = (C.c_int64 * 2)(*a.shape)
+        L.check(self.lib.wlk_qwen_load_tensor(self.h, b"mel_filters", _ptr(a), shape, 2))
+
+    def _mel_call(self, sids, audios, flush: bool) -> List[np.ndarray]:
+        n = len(sids)
+        D = self.dims
+        parts = [np.ascontiguousarray(a, np.float32).reshape(-1) for a in audios] if not flush else [np.zeros(0, np.float32)] * n
+        offs = np.zeros(n + 1, np.int64)
+        offs[1:] = np.cumsum([p.shape[0] for p in parts])
+        flat = np.concatenate(parts) if offs[-1] else np.zeros(1, np.float32)
+        cap = int(offs[-1] // 160 + 4 * n + 8) if not flush else 4 * n + 8
+        out = np.zeros((cap, D.n_mels), np.float32)
+        rows = np.zeros(n + 1, np.int32)
+        ids = np.asarray(list(sids), np.int32)
+        L.check(self.lib.wlk_qwen_append_audio(self.h, _ptr(ids), n, _ptr(flat), _ptr(offs), _ptr(out), cap, _ptr(rows), int(flush)))
+        return [out[rows[i]: rows[i + 1]].copy() for i in range(n)]
+
+    def append_audio(self, sids: Sequence[int], audios: Sequence[np.ndarray]) -> List[np.ndarray]:
+        """StreamingMelExtractor.append per session: raw samples in, newly determined mel frames [frames, n_mels] out."""
+        return self._mel_call(sids, audios, False)
+
+    def flush_audio(self, sids: Sequence[int]) -> List[np.ndarray]:
+        """StreamingMelExtractor.flush per session."""
+        return self._mel_call(sids, None, True)
+
     def flush_pending(self, sids: Sequence[int]) -> List[np.ndarray]:
         """End of stream (causal.py:687-711): encode the buffered whole chunks, drop the sub-chunk remainder."""
         n = len(sids)
