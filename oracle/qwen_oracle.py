@@ -63,11 +63,11 @@ class QwenTowerOracle:
             s["mel"] = StreamingMelOracle(self._filters)
         return s["mel"]
 
-    def append_audio(self, sids, audios):
+    def mel_append(self, sids, audios):
         out = [self._mel(sid).append(a) for sid, a in zip(sids, audios)]
         return [np.zeros((0, self.dims.n_mels), np.float32) if m is None else m for m in out]
 
-    def flush_audio(self, sids):
+    def mel_flush(self, sids):
         out = [self._mel(sid).flush() for sid in sids]
         return [np.zeros((0, self.dims.n_mels), np.float32) if m is None else m for m in out]
 

@@ -161,3 +161,44 @@ def test_shim_over_the_oracle_matches_direct_calls():
     be.close()
     assert got == direct
     assert be.stats["max_sessions_in_call"] >= 2
+
+
+def test_qwen_tower_calls_are_coalesced_too():
+    """The same shim in front of the Qwen3 tower engine API (forward_chunk / append_audio per stream from worker
+    threads): outputs equal the sequential run, calls are merged."""
+    from oracle.make_golden_qwen import mel_stream
+    from oracle.qwen_oracle import QwenTowerOracle
+    from whisperlivekit_b200.qwen_dims import QWEN_DIMS, synthetic_tower_state_dict
+    dims = QWEN_DIMS["qnano"]
+    sd = synthetic_tower_state_dict(dims, seed=2)
+    mels = mel_stream(1500, dims.n_mels, seed=6)
+
+    def drive(engine, threaded):
+        sids = [engine.open_session() for _ in range(4)]
+        out = [[] for _ in sids]
+
+        def run(i):
+            pos = 100 * i
+            for _ in range(6):
+                out[i].append(engine.forward_chunk([sids[i]], [mels[pos: pos + 100 + 7 * i]])[0])
+                pos += 100 + 7 * i
+            out[i].append(engine.flush_pending([sids[i]])[0])
+
+        if threaded:
+            ths = [threading.Thread(target=run, args=(i,)) for i in range(4)]
+            [t.start() for t in ths]
+            [t.join(timeout=120) for t in ths]
+            assert not any(t.is_alive() for t in ths)
+        else:
+            for i in range(4):
+                run(i)
+        return out
+
+    direct = drive(QwenTowerOracle(dims, sd), False)
+    be = BatchingEngine(QwenTowerOracle(dims, sd), max_batch=4, max_wait_s=0.05)
+    got = drive(be, True)
+    be.close()
+    for a, b in zip(got, direct):
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and (x.size == 0 or np.abs(x - y).max() < 1e-6)
+    assert be.stats["by_op"]["forward_chunk"]["calls"] < 24 and be.stats["max_sessions_in_call"] >= 2

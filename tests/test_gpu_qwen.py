@@ -121,12 +121,12 @@ def test_device_mel_front_end_matches_reference_extractor():
     seen = [0]
 
     def append(a):
-        m = eng.append_audio([s], [a])[0]
+        m = eng.mel_append([s], [a])[0]
         seen[0] += m.shape[0]
         return m
 
     def flush():
-        m = eng.flush_audio([s])[0]
+        m = eng.mel_flush([s])[0]
         seen[0] += m.shape[0]
         return m
 
@@ -159,7 +159,7 @@ def test_audio_to_tower_end_to_end_batched():
         for i in range(3):
             parts.append(audio[i][pos[i]: pos[i] + chunk[i]])
             pos[i] += chunk[i]
-        mels = eng.append_audio(sids, parts)
+        mels = eng.mel_append(sids, parts)
         got = eng.forward_chunk(sids, mels)
         for i in range(3):
             m = omel[i].append(parts[i])

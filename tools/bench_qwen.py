@@ -27,7 +27,7 @@ eng.forward_chunk(sids, [mel[: int(p)] for p in phase])             # stagger th
 def tick(k):
     if AUDIO:                                                       # 0.25 s = 4000 samples per stream
         chunks = [pcm[(4000 * k + 997 * i) % 500000: (4000 * k + 997 * i) % 500000 + 4000] for i in range(B)]
-        return eng.forward_chunk(sids, eng.append_audio(sids, chunks))
+        return eng.forward_chunk(sids, eng.mel_append(sids, chunks))
     return eng.forward_chunk(sids, [mel[(37 * k + i) % 4000: (37 * k + i) % 4000 + 25] for i in range(B)])
 
 

@@ -29,8 +29,17 @@ from collections import OrderedDict
 from concurrent.futures import Future
 from typing import Any, Dict, List, Sequence, Tuple
 
-# op name -> how to merge single-session requests into one engine call and split the result
-_BATCHED = ("encode", "decode", "no_speech_prob", "suppress", "greedy_and_align")
+# op name -> (takes one payload item per session, takes one payload shared by the batch).  Single-session requests of
+# one op (and equal static arguments) are merged into one engine call over the concatenated sessions.
+_OPS = {
+    # WhisperEngine (AlignAtt hooks)
+    "encode": (False, False), "decode": (True, False), "no_speech_prob": (False, False), "suppress": (False, True),
+    "greedy_and_align": (False, False),
+    # QwenTowerEngine (QwenAudioCausalKVEncoder.forward_chunk / StreamingMelExtractor.append per stream: mel_append)
+    "forward_chunk": (True, False), "mel_append": (True, False), "mel_flush": (False, False),
+    "flush_pending": (False, False),
+}
+_BATCHED = tuple(_OPS)
 
 
 class _Request:
@@ -115,6 +124,19 @@ class BatchingEngine:
     def greedy_and_align(self, sids, window_iters: int = 16):
         return self.submit("greedy_and_align", sids, window_iters=int(window_iters)).result()
 
+    # Qwen3 tower engine
+    def forward_chunk(self, sids, mels):
+        return self.submit("forward_chunk", sids, list(mels)).result()
+
+    def mel_append(self, sids, audios):
+        return self.submit("mel_append", sids, list(audios)).result()
+
+    def mel_flush(self, sids):
+        return self.submit("mel_flush", sids).result()
+
+    def flush_pending(self, sids):
+        return self.submit("flush_pending", sids).result()
+
     # -- dispatcher -----------------------------------------------------------------------------------------
     def _take_batch(self) -> List[_Request]:
         """Called with the condition held and at least one request pending: wait for companions of the oldest
@@ -158,19 +180,15 @@ class BatchingEngine:
         op = batch[0].op
         sids = [s for r in batch for s in r.sids]
         payload, static = batch[0].payload
+        per_session, shared = _OPS[op]
         try:
+            args = [sids]
+            if per_session:
+                args.append([item for r in batch for item in r.payload[0][0]])
+            if shared:
+                args.append(list(payload[0]))
             with self._lock:
-                if op == "encode":
-                    out = self.engine.encode(sids)
-                elif op == "decode":
-                    toks = [t for r in batch for t in r.payload[0][0]]
-                    out = self.engine.decode(sids, toks, **static)
-                elif op == "no_speech_prob":
-                    out = self.engine.no_speech_prob(sids)
-                elif op == "suppress":
-                    out = self.engine.suppress(sids, list(payload[0]))
-                else:
-                    out = self.engine.greedy_and_align(sids, **static)
+                out = getattr(self.engine, op)(*args, **static)
         except BaseException as e:                      # delivered to the callers of this batch only
             for r in batch:
                 r.future.set_exception(e)

@@ -112,11 +112,11 @@ class QwenTowerEngine:
         L.check(self.lib.wlk_qwen_append_audio(self.h, _ptr(ids), n, _ptr(flat), _ptr(offs), _ptr(out), cap, _ptr(rows), int(flush)))
         return [out[rows[i]: rows[i + 1]].copy() for i in range(n)]
 
-    def append_audio(self, sids: Sequence[int], audios: Sequence[np.ndarray]) -> List[np.ndarray]:
+    def mel_append(self, sids: Sequence[int], audios: Sequence[np.ndarray]) -> List[np.ndarray]:
         """StreamingMelExtractor.append per session: raw samples in, newly determined mel frames [frames, n_mels] out."""
         return self._mel_call(sids, audios, False)
 
-    def flush_audio(self, sids: Sequence[int]) -> List[np.ndarray]:
+    def mel_flush(self, sids: Sequence[int]) -> List[np.ndarray]:
         """StreamingMelExtractor.flush per session."""
         return self._mel_call(sids, None, True)
 

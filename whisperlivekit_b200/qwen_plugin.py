@@ -154,10 +154,10 @@ class B200StreamingMelExtractor:
         return None if m.shape[0] == 0 else torch.from_numpy(m)[None]          # [1, frames, n_mels] like the reference
 
     def append(self, audio):
-        return self._wrap(self.engine.append_audio([self.sid], [np.asarray(audio, np.float32)])[0])
+        return self._wrap(self.engine.mel_append([self.sid], [np.asarray(audio, np.float32)])[0])
 
     def flush(self):
-        return self._wrap(self.engine.flush_audio([self.sid])[0])
+        return self._wrap(self.engine.mel_flush([self.sid])[0])
 
     def reset(self) -> None:
         self.engine.reset_session(self.sid)
