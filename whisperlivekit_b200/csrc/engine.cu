@@ -1003,6 +1003,8 @@ int wlk_engine_set_alignment_heads(wlk_engine* e, const int32_t* pairs, int n_pa
         e->align_rank_host[(size_t)l * e->dims.n_text_head + h] = i;
     }
     e->n_align = n_pairs;
+    for (auto& kv : e->dec_graphs) cudaGraphExecDestroy(kv.second);       // captured launches bake the head count in
+    e->dec_graphs.clear(); e->dec_graph_seen.clear();
     CUDA_CHECK(cudaMemcpy(e->align_rank_dev, e->align_rank_host.data(), e->align_rank_host.size() * 4, cudaMemcpyHostToDevice));
     WLK_API_END
 }
