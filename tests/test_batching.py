@@ -202,3 +202,30 @@ def test_qwen_tower_calls_are_coalesced_too():
         for x, y in zip(a, b):
             assert x.shape == y.shape and (x.size == 0 or np.abs(x - y).max() < 1e-6)
     assert be.stats["by_op"]["forward_chunk"]["calls"] < 24 and be.stats["max_sessions_in_call"] >= 2
+
+
+def test_asyncio_callers_need_no_thread_per_stream():
+    """submit() hands back a concurrent Future: an event loop awaits many streams' calls at once on ONE thread (the
+    reference parks a worker thread per stream, audio_processor.py:543-551) and they are still merged."""
+    import asyncio
+    from whisperlivekit_b200.dims import DIMS
+    inner = CountingEngine(DIMS["micro"])
+    sids = [inner.open_session() for _ in range(16)]
+    for s in sids:
+        inner.append_audio(s, np.zeros(16000 + 320 * s, np.float32))
+    be = BatchingEngine(inner, max_batch=16, max_wait_s=0.05)
+
+    async def stream(sid):
+        content = (await asyncio.wrap_future(be.submit("encode", [sid])))[0]
+        await asyncio.wrap_future(be.submit("decode", [sid], [[1, 2, 3]], sot_index=0))
+        tok = (await asyncio.wrap_future(be.submit("greedy_and_align", [sid], window_iters=16)))[0]
+        return content, tok[0]
+
+    async def main():
+        return await asyncio.gather(*[stream(s) for s in sids])
+
+    res = asyncio.run(main())
+    be.close()
+    assert [r[0] for r in res] == [(16000 + 320 * s) // 320 for s in sids]
+    assert [r[1] for r in res] == [1000 + 37 * s + 1 for s in sids]
+    assert be.stats["max_sessions_in_call"] >= 8 and be.stats["calls"] <= 12
