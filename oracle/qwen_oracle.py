@@ -16,7 +16,7 @@ Nothing outside tests/, __graft_entry__.smoke() and bench.py's CPU arms may impo
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Sequence
 
 import numpy as np
 import torch

@@ -19,7 +19,6 @@ reference's own tests hold no golden logits/tokens.
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np

@@ -25,9 +25,8 @@ from __future__ import annotations
 
 import threading
 import time
-from collections import OrderedDict
 from concurrent.futures import Future
-from typing import Any, Dict, List, Sequence, Tuple
+from typing import Any, Dict, List, Sequence
 
 # op name -> (takes one payload item per session, takes one payload shared by the batch).  Single-session requests of
 # one op (and equal static arguments) are merged into one engine call over the concatenated sessions.

@@ -10,7 +10,7 @@ without a B200.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 

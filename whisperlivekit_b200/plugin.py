@@ -10,7 +10,6 @@ WhisperLiveKit is modified on disk: ``install()`` swaps the ``AlignAtt`` symbol 
 """
 from __future__ import annotations
 
-from typing import Optional
 
 from .dims import ModelDimensions
 from .weights import state_dict_from_torch

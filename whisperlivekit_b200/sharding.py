@@ -5,7 +5,7 @@ at init; afterwards every rank serves its own sessions (sticky placement, weak s
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence
+from typing import Dict, List
 
 
 def shard_streams(n_streams: int, world: int) -> List[List[int]]:
