@@ -53,3 +53,58 @@ def test_two_rank_broadcast_and_sharding():
     assert res[0][1] == res[1][1] != 0
     assert res[0][2] == [0, 1, 2, 3, 4] and res[1][2] == [5, 6, 7, 8]
     assert res[0][3] == res[1][3] == 2.0
+
+
+def _qwen_worker(rank, world, port, q):
+    """Each rank serves its shard of the streams with its own tower (weights broadcast from rank 0 as a flat blob),
+    no exchange on the data path; rank-local results go back to the parent for comparison."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.make_golden_qwen import mel_stream
+    from oracle.qwen_oracle import QwenTowerOracle
+    from whisperlivekit_b200.qwen_dims import QWEN_DIMS, synthetic_tower_state_dict
+    dims = QWEN_DIMS["qnano"]
+    ref_sd = synthetic_tower_state_dict(dims, seed=4)
+    names = sorted(ref_sd)
+    sizes = [ref_sd[k].size for k in names]
+    blob = torch.zeros(sum(sizes), dtype=torch.float32)
+    if rank == 0:
+        blob.copy_(torch.from_numpy(np.concatenate([ref_sd[k].reshape(-1) for k in names])))
+    broadcast_blob(blob, src=0)                                   # the only collective: weights at init
+    sd, off = {}, 0
+    for k, n in zip(names, sizes):
+        sd[k] = blob[off: off + n].numpy().reshape(ref_sd[k].shape).copy()
+        off += n
+    eng = QwenTowerOracle(dims, sd)
+    mine = shard_streams(5, world)[rank]
+    out = {}
+    for stream in mine:
+        sid = eng.open_session()
+        mels = mel_stream(450, dims.n_mels, seed=100 + stream)
+        rows = [eng.forward_chunk([sid], [mels[a: a + 150]])[0] for a in range(0, 450, 150)]
+        out[stream] = np.concatenate(rows, axis=0)
+    q.put((rank, {k: v.tolist() for k, v in out.items()}))
+    dist.destroy_process_group()
+
+
+def test_two_rank_qwen_streams_are_sharded_without_data_exchange():
+    from oracle.make_golden_qwen import mel_stream
+    from oracle.qwen_oracle import QwenTowerOracle
+    from whisperlivekit_b200.qwen_dims import QWEN_DIMS, synthetic_tower_state_dict
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_qwen_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(x for _, d in sorted(q.get(timeout=300) for _ in procs) for x in d.items())
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [0, 1, 2, 3, 4]
+    dims = QWEN_DIMS["qnano"]
+    eng = QwenTowerOracle(dims, synthetic_tower_state_dict(dims, seed=4))
+    for stream in range(5):
+        sid = eng.open_session()
+        mels = mel_stream(450, dims.n_mels, seed=100 + stream)
+        want = np.concatenate([eng.forward_chunk([sid], [mels[a: a + 150]])[0] for a in range(0, 450, 150)], axis=0)
+        np.testing.assert_allclose(np.asarray(res[stream], np.float32), want, atol=1e-6)
