@@ -33,8 +33,11 @@ typedef struct wlk_dims {
     int32_t n_vocab, n_text_ctx, n_text_state, n_text_head, n_text_layer;
 } wlk_dims;
 
-enum { WLK_PREC_FP32 = 0,   /* SIMT fp32 kernels end to end: the 1e-3-on-logits parity mode      */
-       WLK_PREC_BF16 = 1 }; /* bf16 operands / fp32 accumulate + fp32 residual: the serving mode  */
+enum { WLK_PREC_FP32 = 0,     /* SIMT fp32 kernels end to end: the 1e-3-on-logits parity mode                    */
+       WLK_PREC_BF16 = 1,     /* bf16 operands / fp32 accumulate + fp32 residual: the serving mode                */
+       WLK_PREC_BF16X3 = 2 }; /* tcgen05 with split operands (x = hi + lo, both bf16; A_hi W_hi + A_lo W_hi +    *
+                               * A_hi W_lo into one fp32 accumulator): 1e-3 on logits at tensor-core speed / 3;   *
+                               * activations, softmax, LayerNorm and K/V caches stay fp32                         */
 enum { WLK_BACKEND_AUTO = 0, WLK_BACKEND_SIMT = 1, WLK_BACKEND_TCGEN05 = 2 };
 
 typedef struct wlk_config {

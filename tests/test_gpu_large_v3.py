@@ -1,0 +1,150 @@
+"""GPU: the BENCHMARKED geometry (large-v3) in the benchmarked precision mode (bf16 tcgen05) -- and the exact
+modes -- against tests/golden/large_v3_forced.npz, which oracle/make_golden_large.py recorded from the REAL
+reference (vendored torch Whisper + AlignAtt hooks, fp32 CPU) on seeded weights at true large-v3 dims.
+
+What runs: two streams of different length batched in every call (CTA-pair GEMM for the wide encoder GEMMs, the
+one-CTA GEMM for the N=1280 ones, attn_tc), a 20-token prefill (tcgen05 cross-attention for the non-alignment
+heads), then 64 single-token steps (split-K decoder GEMMs, CUDA-graph replay from the third step on), each with
+the AlignAtt suppression set, the DRY penalty, greedy pick and the alignment-head reduction over the last 16
+iterations.  The engine is teacher-forced with the reference's token so every step is compared on equal input.
+
+Criteria (north_star: "within 1e-3 on logits / identical committed token sequences"):
+  fp32  mode  : |dlogits| <= 1e-3, tokens and attended frames identical.
+  bf16x3 mode : |dlogits| <= 1e-3, tokens and attended frames identical   (tcgen05, split operands, 3 MMAs).
+  bf16  mode  : token identical to the reference at every step whose reference top-2 gap exceeds EPS_GAP
+                (= 4 x the measured max |dlogits| of the mode); attended frame identical or within FRAME_TOL
+                frames at >= 90 % of the steps; max |dlogits| reported and bounded by BF16_LOGIT_TOL.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from golden_util import GOLDEN
+from whisperlivekit_b200.alignatt import dry_penalties
+from whisperlivekit_b200.dims import ModelDimensions
+from whisperlivekit_b200.weights import synthetic_audio, synthetic_state_dict
+
+BF16_LOGIT_TOL = 0.15      # bf16 operands through 32 + 32 layers on logits of std 3 (measured: see profiles/r02_parity_large_v3.json)
+EPS_GAP = 0.5              # reference top-2 gap above which the bf16 mode must pick the same token
+FRAME_TOL = 2
+_STATE = {}
+
+
+def fixture():
+    if "g" not in _STATE:
+        g = dict(np.load(os.path.join(GOLDEN, "large_v3_forced.npz")))
+        dims = ModelDimensions(*[int(x) for x in g["dims"]])
+        _STATE["g"] = g
+        _STATE["dims"] = dims
+        _STATE["sd"] = synthetic_state_dict(dims, seed=int(g["weight_seed"]))
+        _STATE["heads"] = [tuple(int(v) for v in r) for r in g["align_heads"]]
+    return _STATE["g"], _STATE["dims"], _STATE["sd"], _STATE["heads"]
+
+
+def sample(g, key, arr):
+    a = np.asarray(arr, np.float32).reshape(-1)[g[key + "__idx"]]
+    ref = g[key + "__val"]
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(a), fin), key
+    return float(np.abs(a[fin] - ref[fin]).max())
+
+
+def run_mode(precision):
+    """-> per-stream dict(tokens, frames, top_err [steps], sample_err {step: err}, enc_err)"""
+    from whisperlivekit_b200.engine import WhisperEngine
+    g, dims, sd, heads = fixture()
+    n_streams, n_steps = int(g["n_streams"]), int(g["n_steps"])
+    prefix = [int(t) for t in g["prefix"]]
+    suppress = [int(t) for t in g["suppress_tokens"]]
+    blank = [int(t) for t in g["blank_tokens"]]
+    eng = WhisperEngine(dims, sd, heads, precision=precision, max_sessions=n_streams, max_batch=n_streams)
+    sids = [eng.open_session() for _ in range(n_streams)]
+    for i, s in enumerate(sids):
+        eng.append_audio(s, synthetic_audio(float(g["audio_seconds"][i]), seed=int(g["audio_seeds"][i])))
+    content = eng.encode(sids)
+    res = [dict(tokens=[], frames=[], top_err=[], sample_err={}, logprob_err=[]) for _ in sids]
+    for i, s in enumerate(sids):
+        assert content[i] == int(g[f"s{i}_content"])
+        res[i]["enc_err"] = sample(g, f"s{i}_enc", eng.read_encoder(s))
+    current = [list(prefix) for _ in sids]
+    feed = [list(prefix) for _ in sids]
+    for it in range(n_steps):
+        eng.decode(sids, feed, sot_index=0)
+        if it == 0:
+            for i, s in enumerate(sids):
+                res[i]["sot_err"] = sample(g, f"s{i}_logits_sot", eng.read_sot_logits(s))
+            eng.suppress(sids, blank)
+        eng.suppress(sids, suppress)
+        for i, s in enumerate(sids):
+            pen = dry_penalties(current[i], eng.specials.eot)
+            if pen:
+                eng.add_logit_bias(s, [t for t, _ in pen], [-a for _, a in pen])
+        out = eng.greedy_and_align(sids, window_iters=16)
+        for i, s in enumerate(sids):
+            lg = eng.read_logits(s)
+            ids, vals = g[f"s{i}_top_ids"][it], g[f"s{i}_top_vals"][it]
+            res[i]["top_err"].append(float(np.abs(lg[ids] - vals).max()))
+            if f"s{i}_logits_step{it}__idx" in g:
+                res[i]["sample_err"][it] = sample(g, f"s{i}_logits_step{it}", lg)
+            res[i]["tokens"].append(out[i][0])
+            res[i]["frames"].append(out[i][2])
+            res[i]["logprob_err"].append(abs(out[i][1] - float(g[f"s{i}_logprobs"][it])))
+            tok = int(g[f"s{i}_tokens"][it])                  # teacher forcing with the reference's choice
+            feed[i] = [tok]
+            current[i].append(tok)
+    eng.close()
+    return res
+
+
+def summarise(precision, res):
+    g = fixture()[0]
+    out = dict(mode=precision, streams=[])
+    for i, r in enumerate(res):
+        ref_t, ref_f, gaps = g[f"s{i}_tokens"], g[f"s{i}_frames"], g[f"s{i}_gaps"]
+        tok_eq = np.asarray(r["tokens"]) == ref_t
+        fr_d = np.abs(np.asarray(r["frames"]) - ref_f)
+        out["streams"].append(dict(
+            max_abs_dlogits_top8=max(r["top_err"]), max_abs_dlogits_sampled=max(r["sample_err"].values()),
+            enc_err=r["enc_err"], sot_err=r["sot_err"], max_logprob_err=max(r["logprob_err"]),
+            tokens_identical=int(tok_eq.sum()), steps=len(ref_t),
+            mismatch_gaps=[float(x) for x in gaps[~tok_eq]], min_ref_gap=float(gaps.min()),
+            frames_identical=int((fr_d == 0).sum()), frames_within_tol=int((fr_d <= FRAME_TOL).sum()),
+            max_frame_delta=int(fr_d.max())))
+    os.makedirs(os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out", f"parity_large_v3_{precision}.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print(json.dumps(out))
+    return out
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_large_v3_exact_modes_match_reference(precision):
+    res = run_mode(precision)
+    rep = summarise(precision, res)
+    g = fixture()[0]
+    for i, (r, s) in enumerate(zip(res, rep["streams"])):
+        assert s["max_abs_dlogits_top8"] <= 1e-3, s
+        assert s["max_abs_dlogits_sampled"] <= 1e-3, s
+        assert s["sot_err"] <= 1e-3 and s["enc_err"] <= 1e-3, s
+        assert r["tokens"] == [int(t) for t in g[f"s{i}_tokens"]]
+        assert r["frames"] == [int(t) for t in g[f"s{i}_frames"]]
+        assert s["max_logprob_err"] <= 1e-3
+
+
+def test_large_v3_bf16_serving_mode_tokens_match_reference():
+    res = run_mode("bf16")
+    rep = summarise("bf16", res)
+    g = fixture()[0]
+    for i, (r, s) in enumerate(zip(res, rep["streams"])):
+        gaps = g[f"s{i}_gaps"]
+        ref_t = g[f"s{i}_tokens"]
+        assert s["max_abs_dlogits_top8"] <= BF16_LOGIT_TOL, s
+        assert EPS_GAP >= 3.0 * s["max_abs_dlogits_top8"], ("EPS_GAP no longer covers the measured error", s)
+        for it in range(len(ref_t)):
+            if gaps[it] > EPS_GAP:
+                assert r["tokens"][it] == int(ref_t[it]), (i, it, float(gaps[it]), r["tokens"][it], int(ref_t[it]))
+        assert s["frames_within_tol"] >= 0.9 * s["steps"], s

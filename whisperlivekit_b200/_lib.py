@@ -30,7 +30,7 @@ class wlk_config(C.Structure):
         "max_align_heads", "reserved")]
 
 
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
 BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
 KERNEL_CLASSES = ["mel", "gemm_enc", "attn_enc", "layernorm", "gemm_xkv", "gemm_dec",
                   "attn_dec_self", "attn_dec_cross", "logits", "align", "misc"]

@@ -7,6 +7,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 
 namespace wlk {
@@ -68,17 +69,20 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // True the first time it is called for the current device with this flag array: kernel attributes (dynamic shared
 // memory limits) and scratch allocations are per device, and several engines -- one per GPU -- may live in a process.
 inline bool first_on_device(bool (&seen)[64]) {
+    static std::mutex mu;                       // engines on different threads may race to the first launch
     int d = 0;
     cudaGetDevice(&d);
     d &= 63;
+    std::lock_guard<std::mutex> lk(mu);
     if (seen[d]) return false;
     seen[d] = true;
     return true;
 }
 inline int current_device() { int d = 0; cudaGetDevice(&d); return d & 63; }
 
-enum DType { DT_F32 = 0, DT_BF16 = 1 };
-inline size_t dtype_size(int t) { return t == DT_F32 ? 4 : 2; }
+// DT_BF16X2: weights of the WLK_PREC_BF16X3 mode -- two bf16 planes (hi, then lo right behind it), 4 bytes per element
+enum DType { DT_F32 = 0, DT_BF16 = 1, DT_BF16X2 = 2 };
+inline size_t dtype_size(int t) { return t == DT_BF16 ? 2 : 4; }
 
 // ---------------------------------------------------------------------------------
 // GEMM epilogue description shared by the SIMT and the tcgen05 GEMM kernels.
@@ -119,13 +123,22 @@ struct Epilogue {
 struct GemmArgs {
     const void* A = nullptr; int a_type = DT_F32; int64_t lda = 0;   // [M, K] row-major (K contiguous)
     const void* W = nullptr; int w_type = DT_F32; int64_t ldw = 0;   // [N, K] row-major (K contiguous)
+    const void* W_lo = nullptr;          // DT_BF16X2: the lo plane (W is the hi plane)
+    void* a_split = nullptr;             // DT_BF16X2: scratch for the (hi, lo) planes of the fp32 A operand,
+    size_t a_split_elems = 0;            //            a_split_elems bf16 per plane
     int M = 0, N = 0, K = 0;
     Epilogue epi;
+    // split-K workspace of the CALLING engine (its stream orders the launches that share it): fp32 partial tiles and
+    // one arrival counter per output tile, zero between launches.  Null: the GEMM runs unsplit.
+    float* sk_scratch = nullptr; size_t sk_scratch_floats = 0;
+    int* sk_counters = nullptr; int sk_max_tiles = 0;
 };
+constexpr size_t SK_SCRATCH_FLOATS = (size_t)8 << 20;     // 32 MB per engine
+constexpr int SK_MAX_TILES = 4096;
 
 void gemm_simt(const GemmArgs& g, cudaStream_t st);
 void gemm_tcgen05(const GemmArgs& g, cudaStream_t st, int num_sms, int variant = 0);   // 0 auto, 1 one-CTA, 2 CTA pair
-void gemm_tcgen05_pair(const GemmArgs& g, cudaStream_t st, int num_sms);
+void gemm_tcgen05_pair(const GemmArgs& g, const void* A_hi, const void* A_lo, cudaStream_t st, int num_sms);
 bool gemm_tcgen05_supported(const GemmArgs& g, std::string* why);
 
 // ---------------------------------------------------------------------------------

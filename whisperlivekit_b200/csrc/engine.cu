@@ -1,6 +1,7 @@
 // Engine: weights arena, per-session device state, batched encode/decode orchestration and the C ABI
 // declared in include/wlk_b200.h.  One CUDA stream per engine; calls are serialised by a mutex and
 // concurrency comes from batching sessions into one call.
+#include <algorithm>
 #include <cmath>
 #include <map>
 #include <mutex>
@@ -83,7 +84,9 @@ using namespace wlk;
 struct wlk_engine {
     wlk_dims dims{};
     wlk_config cfg{};
-    int act = DT_F32;                 // activation / weight-matrix type
+    int act = DT_F32;                 // activation type (and type of every session buffer)
+    int wt = DT_F32;                  // weight-matrix type: = act, or DT_BF16X2 (hi + lo bf16 planes) in WLK_PREC_BF16X3
+    void* a_split = nullptr; size_t a_split_elems = 0;   // BF16X3: (hi, lo) planes of a GEMM's fp32 activation operand
     int gemm_backend = WLK_BACKEND_SIMT, attn_backend = WLK_BACKEND_SIMT;
     int num_sms = 148;
     cudaStream_t st = nullptr;
@@ -91,8 +94,10 @@ struct wlk_engine {
     // token-step CUDA graphs: the ~390 launches of one decoder step depend only on the batch size (every per-session
     // quantity travels in the staged job arrays), so they are captured once per batch size and replayed
     bool graphs_on = true;
-    std::map<uint64_t, cudaGraphExec_t> dec_graphs;
+    struct GraphSlot { cudaGraphExec_t exec; uint64_t last_use; };
+    std::map<uint64_t, GraphSlot> dec_graphs;     // LRU-bounded: under the batching shim the batch size varies in 1..max_batch
     std::set<uint64_t> dec_graph_seen;
+    uint64_t dec_graph_tick = 0;
 
     Arena arena;
     Weights w;
@@ -113,6 +118,7 @@ struct wlk_engine {
     void** xptrs_dev = nullptr;               // x + b*1500*d
     float* audio_scratch = nullptr;
     void* beam_scratch = nullptr; size_t beam_scratch_cap = 0;   // staging for wlk_sessions_gather_decoder
+    float* sk_scratch = nullptr; int* sk_counters = nullptr;     // this engine's split-K workspace (GemmArgs)
     float* mel_scratch = nullptr;             // fp32 [MEL_ROWS][n_mels] for the read_mel tap
     // decoder workspace
     int dec_rows_max = 0;
@@ -131,6 +137,7 @@ struct wlk_engine {
     size_t bytes_weights = 0, bytes_sessions = 0, bytes_workspace = 0;
 
     size_t es() const { return dtype_size(act); }
+    size_t wes() const { return dtype_size(wt); }
 };
 
 namespace wlk {
@@ -179,7 +186,7 @@ void layout_weights(wlk_engine* e) {
     const wlk_dims& D = e->dims;
     Arena& A = e->arena;
     Weights& W = e->w;
-    const size_t es = e->es();
+    const size_t es = e->wes();
     const int d = D.n_audio_state, dt = D.n_text_state;
     auto f32 = [&](size_t n) { return reinterpret_cast<float*>(A.take(n * 4)); };
     auto mat = [&](size_t n) { return A.take(n * es); };
@@ -201,7 +208,7 @@ void layout_weights(wlk_engine* e) {
     }
     W.lnpw = f32(d); W.lnpb = f32(d);
     W.emb_f32 = f32((size_t)D.n_vocab * dt);
-    W.emb_act = (e->act == DT_F32) ? (void*)W.emb_f32 : mat((size_t)D.n_vocab * dt);
+    W.emb_act = (e->wt == DT_F32) ? (void*)W.emb_f32 : mat((size_t)D.n_vocab * dt);
     W.dec_pos = f32((size_t)D.n_text_ctx * dt);
     W.dec.resize(D.n_text_layer);
     for (auto& l : W.dec) {
@@ -220,26 +227,51 @@ void layout_weights(wlk_engine* e) {
     W.bxkv = f32((size_t)D.n_text_layer * 2 * dt);
 }
 
-float* stage(wlk_engine* e, const float* host, size_t n) {
+float* stage_reserve(wlk_engine* e, size_t n) {
     if (n > e->stage_cap) {
         if (e->stage_f32) CUDA_CHECK(cudaFree(e->stage_f32));
         size_t cap = n < (1u << 20) ? (1u << 20) : n;
         CUDA_CHECK(cudaMalloc(&e->stage_f32, cap * 4));
         e->stage_cap = cap;
     }
-    CUDA_CHECK(cudaMemcpyAsync(e->stage_f32, host, n * 4, cudaMemcpyHostToDevice, e->st));
     return e->stage_f32;
+}
+float* stage(wlk_engine* e, const float* host, size_t n) {
+    float* s = stage_reserve(e, n);
+    CUDA_CHECK(cudaMemcpyAsync(s, host, n * 4, cudaMemcpyHostToDevice, e->st));
+    return s;
 }
 void put_f32(wlk_engine* e, float* dst, const float* host, size_t n) {
     CUDA_CHECK(cudaMemcpyAsync(dst, host, n * 4, cudaMemcpyHostToDevice, e->st));
     CUDA_CHECK(cudaStreamSynchronize(e->st));
 }
-void put_mat(wlk_engine* e, void* dst, const float* host, size_t n) {
-    float* s = stage(e, host, n);
-    convert_f32_to(s, dst, e->act, (int64_t)n, e->st);
+// device fp32 -> `n` elements at element offset `off` of a weight matrix of `total` elements (planar in DT_BF16X2)
+void store_mat(wlk_engine* e, void* base, size_t total, size_t off, const float* src_dev, size_t n) {
+    if (e->wt == DT_BF16X2) {
+        bf16* hi = reinterpret_cast<bf16*>(base) + off;
+        split_f32_to_planes(src_dev, hi, hi + total, (int64_t)n, e->st);
+    } else {
+        convert_f32_to(src_dev, reinterpret_cast<uint8_t*>(base) + off * e->wes(), e->wt, (int64_t)n, e->st);
+    }
     CUDA_CHECK(cudaStreamSynchronize(e->st));
 }
+void put_mat(wlk_engine* e, void* base, size_t total, size_t off, const float* host, size_t n) {
+    store_mat(e, base, total, off, stage(e, host, n), n);
+}
 uint8_t* offs(void* p, size_t elems, size_t es) { return reinterpret_cast<uint8_t*>(p) + elems * es; }
+// conv weight [c_out, c_in, 3] -> tap-major [c_out, 3 * c_in] in the weight type (via an fp32 staging copy in BF16X3)
+void put_conv(wlk_engine* e, void* dst, const float* host, int c_out, int c_in) {
+    const size_t n = (size_t)c_out * c_in * 3;
+    float* s = stage_reserve(e, 2 * n);                         // second half: the packed fp32 copy
+    CUDA_CHECK(cudaMemcpyAsync(s, host, n * 4, cudaMemcpyHostToDevice, e->st));
+    if (e->wt == DT_BF16X2) {
+        pack_conv_weight(s, s + n, DT_F32, c_out, c_in, e->st);
+        store_mat(e, dst, n, 0, s + n, n);
+    } else {
+        pack_conv_weight(s, dst, e->wt, c_out, c_in, e->st);
+        CUDA_CHECK(cudaStreamSynchronize(e->st));
+    }
+}
 
 int64_t numel(const int64_t* shape, int ndim) {
     int64_t n = 1;
@@ -277,14 +309,10 @@ void load_tensor(wlk_engine* e, const std::string& name, const float* host, cons
         put_f32(e, W.window, host, n);
     } else if (name == "encoder.conv1.weight") {
         expect((int64_t)d * D.n_mels * 3);
-        float* s = stage(e, host, n);
-        pack_conv_weight(s, W.Wc1, e->act, d, D.n_mels, e->st);
-        CUDA_CHECK(cudaStreamSynchronize(e->st));
+        put_conv(e, W.Wc1, host, d, D.n_mels);
     } else if (name == "encoder.conv2.weight") {
         expect((int64_t)d * d * 3);
-        float* s = stage(e, host, n);
-        pack_conv_weight(s, W.Wc2, e->act, d, d, e->st);
-        CUDA_CHECK(cudaStreamSynchronize(e->st));
+        put_conv(e, W.Wc2, host, d, d);
     } else if (name == "encoder.conv1.bias") { expect(d); put_f32(e, W.bc1, host, n);
     } else if (name == "encoder.conv2.bias") { expect(d); put_f32(e, W.bc2, host, n);
     } else if (name == "encoder.positional_embedding") { expect((int64_t)D.n_audio_ctx * d); put_f32(e, W.enc_pos, host, n);
@@ -293,7 +321,7 @@ void load_tensor(wlk_engine* e, const std::string& name, const float* host, cons
     } else if (name == "decoder.token_embedding.weight") {
         expect((int64_t)D.n_vocab * dt);
         put_f32(e, W.emb_f32, host, n);
-        if (e->act != DT_F32) { convert_f32_to(W.emb_f32, W.emb_act, e->act, n, e->st); CUDA_CHECK(cudaStreamSynchronize(e->st)); }
+        if (e->wt != DT_F32) store_mat(e, W.emb_act, (size_t)n, 0, W.emb_f32, (size_t)n);
     } else if (name == "decoder.positional_embedding") { expect((int64_t)D.n_text_ctx * dt); put_f32(e, W.dec_pos, host, n);
     } else if (name == "decoder.ln.weight") { expect(dt); put_f32(e, W.lnw, host, n);
     } else if (name == "decoder.ln.bias") { expect(dt); put_f32(e, W.lnb, host, n);
@@ -307,18 +335,18 @@ void load_tensor(wlk_engine* e, const std::string& name, const float* host, cons
         WLK_CHECK(li >= 0 && li < (is_dec ? D.n_text_layer : D.n_audio_layer), "layer index out of range in %s", name.c_str());
         if (!is_dec) {
             EncLayerW& L = W.enc[li];
-            if (rest == "attn.query.weight") { expect((int64_t)dm * dm); put_mat(e, L.Wqkv, host, n); }
-            else if (rest == "attn.key.weight") { expect((int64_t)dm * dm); put_mat(e, offs(L.Wqkv, (size_t)dm * dm, es), host, n); }
-            else if (rest == "attn.value.weight") { expect((int64_t)dm * dm); put_mat(e, offs(L.Wqkv, (size_t)2 * dm * dm, es), host, n); }
+            if (rest == "attn.query.weight") { expect((int64_t)dm * dm); put_mat(e, L.Wqkv, (size_t)3 * dm * dm, 0, host, n); }
+            else if (rest == "attn.key.weight") { expect((int64_t)dm * dm); put_mat(e, L.Wqkv, (size_t)3 * dm * dm, (size_t)dm * dm, host, n); }
+            else if (rest == "attn.value.weight") { expect((int64_t)dm * dm); put_mat(e, L.Wqkv, (size_t)3 * dm * dm, (size_t)2 * dm * dm, host, n); }
             else if (rest == "attn.query.bias") { expect(dm); put_f32(e, L.bqkv, host, n); }
             else if (rest == "attn.value.bias") { expect(dm); put_f32(e, L.bqkv + 2 * dm, host, n); }
-            else if (rest == "attn.out.weight") { expect((int64_t)dm * dm); put_mat(e, L.Wo, host, n); }
+            else if (rest == "attn.out.weight") { expect((int64_t)dm * dm); put_mat(e, L.Wo, (size_t)dm * dm, 0, host, n); }
             else if (rest == "attn.out.bias") { expect(dm); put_f32(e, L.bo, host, n); }
             else if (rest == "attn_ln.weight") { expect(dm); put_f32(e, L.ln1w, host, n); }
             else if (rest == "attn_ln.bias") { expect(dm); put_f32(e, L.ln1b, host, n); }
-            else if (rest == "mlp.0.weight") { expect((int64_t)4 * dm * dm); put_mat(e, L.W1, host, n); }
+            else if (rest == "mlp.0.weight") { expect((int64_t)4 * dm * dm); put_mat(e, L.W1, (size_t)4 * dm * dm, 0, host, n); }
             else if (rest == "mlp.0.bias") { expect(4 * dm); put_f32(e, L.b1, host, n); }
-            else if (rest == "mlp.2.weight") { expect((int64_t)4 * dm * dm); put_mat(e, L.W2, host, n); }
+            else if (rest == "mlp.2.weight") { expect((int64_t)4 * dm * dm); put_mat(e, L.W2, (size_t)4 * dm * dm, 0, host, n); }
             else if (rest == "mlp.2.bias") { expect(dm); put_f32(e, L.b2, host, n); }
             else if (rest == "mlp_ln.weight") { expect(dm); put_f32(e, L.ln2w, host, n); }
             else if (rest == "mlp_ln.bias") { expect(dm); put_f32(e, L.ln2b, host, n); }
@@ -326,27 +354,27 @@ void load_tensor(wlk_engine* e, const std::string& name, const float* host, cons
         } else {
             DecLayerW& L = W.dec[li];
             const size_t xrow = (size_t)li * 2 * dt;      // row offset inside Wxkv / bxkv
-            if (rest == "attn.query.weight") { expect((int64_t)dm * dm); put_mat(e, L.Wqkv, host, n); }
-            else if (rest == "attn.key.weight") { expect((int64_t)dm * dm); put_mat(e, offs(L.Wqkv, (size_t)dm * dm, es), host, n); }
-            else if (rest == "attn.value.weight") { expect((int64_t)dm * dm); put_mat(e, offs(L.Wqkv, (size_t)2 * dm * dm, es), host, n); }
+            if (rest == "attn.query.weight") { expect((int64_t)dm * dm); put_mat(e, L.Wqkv, (size_t)3 * dm * dm, 0, host, n); }
+            else if (rest == "attn.key.weight") { expect((int64_t)dm * dm); put_mat(e, L.Wqkv, (size_t)3 * dm * dm, (size_t)dm * dm, host, n); }
+            else if (rest == "attn.value.weight") { expect((int64_t)dm * dm); put_mat(e, L.Wqkv, (size_t)3 * dm * dm, (size_t)2 * dm * dm, host, n); }
             else if (rest == "attn.query.bias") { expect(dm); put_f32(e, L.bqkv, host, n); }
             else if (rest == "attn.value.bias") { expect(dm); put_f32(e, L.bqkv + 2 * dm, host, n); }
-            else if (rest == "attn.out.weight") { expect((int64_t)dm * dm); put_mat(e, L.Wo, host, n); }
+            else if (rest == "attn.out.weight") { expect((int64_t)dm * dm); put_mat(e, L.Wo, (size_t)dm * dm, 0, host, n); }
             else if (rest == "attn.out.bias") { expect(dm); put_f32(e, L.bo, host, n); }
             else if (rest == "attn_ln.weight") { expect(dm); put_f32(e, L.ln1w, host, n); }
             else if (rest == "attn_ln.bias") { expect(dm); put_f32(e, L.ln1b, host, n); }
-            else if (rest == "cross_attn.query.weight") { expect((int64_t)dm * dm); put_mat(e, L.Wqc, host, n); }
+            else if (rest == "cross_attn.query.weight") { expect((int64_t)dm * dm); put_mat(e, L.Wqc, (size_t)dm * dm, 0, host, n); }
             else if (rest == "cross_attn.query.bias") { expect(dm); put_f32(e, L.bqc, host, n); }
-            else if (rest == "cross_attn.key.weight") { expect((int64_t)dt * d); put_mat(e, offs(W.Wxkv, xrow * d, es), host, n); }
-            else if (rest == "cross_attn.value.weight") { expect((int64_t)dt * d); put_mat(e, offs(W.Wxkv, (xrow + dt) * d, es), host, n); }
+            else if (rest == "cross_attn.key.weight") { expect((int64_t)dt * d); put_mat(e, W.Wxkv, (size_t)D.n_text_layer * 2 * dt * d, xrow * d, host, n); }
+            else if (rest == "cross_attn.value.weight") { expect((int64_t)dt * d); put_mat(e, W.Wxkv, (size_t)D.n_text_layer * 2 * dt * d, (xrow + dt) * d, host, n); }
             else if (rest == "cross_attn.value.bias") { expect(dt); put_f32(e, W.bxkv + xrow + dt, host, n); }
-            else if (rest == "cross_attn.out.weight") { expect((int64_t)dm * dm); put_mat(e, L.Woc, host, n); }
+            else if (rest == "cross_attn.out.weight") { expect((int64_t)dm * dm); put_mat(e, L.Woc, (size_t)dm * dm, 0, host, n); }
             else if (rest == "cross_attn.out.bias") { expect(dm); put_f32(e, L.boc, host, n); }
             else if (rest == "cross_attn_ln.weight") { expect(dm); put_f32(e, L.lncw, host, n); }
             else if (rest == "cross_attn_ln.bias") { expect(dm); put_f32(e, L.lncb, host, n); }
-            else if (rest == "mlp.0.weight") { expect((int64_t)4 * dm * dm); put_mat(e, L.W1, host, n); }
+            else if (rest == "mlp.0.weight") { expect((int64_t)4 * dm * dm); put_mat(e, L.W1, (size_t)4 * dm * dm, 0, host, n); }
             else if (rest == "mlp.0.bias") { expect(4 * dm); put_f32(e, L.b1, host, n); }
-            else if (rest == "mlp.2.weight") { expect((int64_t)4 * dm * dm); put_mat(e, L.W2, host, n); }
+            else if (rest == "mlp.2.weight") { expect((int64_t)4 * dm * dm); put_mat(e, L.W2, (size_t)4 * dm * dm, 0, host, n); }
             else if (rest == "mlp.2.bias") { expect(dm); put_f32(e, L.b2, host, n); }
             else if (rest == "mlp_ln.weight") { expect(dm); put_f32(e, L.ln2w, host, n); }
             else if (rest == "mlp_ln.bias") { expect(dm); put_f32(e, L.ln2b, host, n); }
@@ -387,6 +415,17 @@ void run_gemm(wlk_engine* e, GemmArgs& g, int cls) {
     ProfScope ps(e, cls, 2.0 * g.M * (double)g.N * g.K,
                  (double)g.M * g.K * dtype_size(g.a_type) + (double)g.N * g.K * dtype_size(g.w_type) +
                      (double)g.M * g.N * dtype_size(g.epi.c_type));
+    g.sk_scratch = e->sk_scratch; g.sk_scratch_floats = SK_SCRATCH_FLOATS;
+    g.sk_counters = e->sk_counters; g.sk_max_tiles = SK_MAX_TILES;
+    if (e->wt == DT_BF16X2) {
+        // every weight matrix is one whole [N, ldw] allocation: the lo plane sits right behind the hi plane
+        g.W_lo = reinterpret_cast<const bf16*>(g.W) + (size_t)g.N * g.ldw;
+        g.a_split = e->a_split; g.a_split_elems = e->a_split_elems;
+        std::string why;
+        WLK_CHECK(gemm_tcgen05_supported(g, &why), "bf16x3 GEMM (M=%d N=%d K=%d): %s", g.M, g.N, g.K, why.c_str());
+        gemm_tcgen05(g, e->st, e->num_sms);
+        return;
+    }
     bool tc = e->gemm_backend == WLK_BACKEND_TCGEN05 && gemm_tcgen05_supported(g, nullptr);
     if (tc) gemm_tcgen05(g, e->st, e->num_sms);
     else gemm_simt(g, e->st);
@@ -435,28 +474,34 @@ void encode_batch(wlk_engine* e, const int32_t* sids, int n, int32_t* content_ou
     const int nm = D.n_mels;
     const size_t es = e->es();
     WLK_CHECK(n >= 1 && n <= e->cfg.max_batch, "encode batch %d outside [1, %d]", n, e->cfg.max_batch);
-    Stager sg(e);
-    MelJob* mj_dev; MelJob* mj = sg.host<MelJob>(n, &mj_dev);
-    void** xkv_dev; void** xkv = sg.host<void*>(n, &xkv_dev);
+    // first pass: validation only (no session state is touched until the whole batch is known to be good)
     for (int i = 0; i < n; ++i) {
         Session& s = get_root_session(e, sids[i], "encode");
         WLK_CHECK(s.audio_len > 0, "session %d has no audio", sids[i]);
         for (int j = 0; j < i; ++j) WLK_CHECK(sids[j] != sids[i], "session %d appears twice in the batch", sids[i]);
+    }
+    Stager sg(e);
+    MelJob* mj_dev; MelJob* mj = sg.host<MelJob>(n, &mj_dev);
+    void** xkv_dev; void** xkv = sg.host<void*>(n, &xkv_dev);
+    int max_frames = 1;
+    for (int i = 0; i < n; ++i) {
+        Session& s = e->sess[sids[i]];
         const int64_t N = s.audio_len;
         const int64_t n_total = (N + 480000) / HOP;                 // torch.stft frames minus the dropped last one
-        int64_t n_compute = (N + 199) / HOP + 1;                   // frames whose window overlaps [0, N)
-        if (n_compute > N_FRAMES + 2) n_compute = N_FRAMES + 2;
+        int64_t n_compute = (N + 199) / HOP + 1;                   // frames whose window overlaps [0, N): all of them
+        if (n_compute > MEL_MAX_FRAMES) n_compute = MEL_MAX_FRAMES; // join the global max, also beyond the 30 s kept
+        if (n_compute > max_frames) max_frames = (int)n_compute;
         mj[i].audio = s.audio; mj[i].raw = s.mel_raw; mj[i].blockmax = s.mel_blockmax;
         mj[i].out = offs(e->mel_t, (size_t)i * MEL_ROWS * nm, es);
         mj[i].n = (int32_t)N; mj[i].n_compute = (int32_t)n_compute; mj[i].n_total = (int32_t)n_total; mj[i].pad = 0;
-        s.content_len = (int)((n_total - N_FRAMES) / 2);            // simul_whisper.py:350
-        content_out[i] = s.content_len;
+        s.content_len = (int)((n_total - N_FRAMES) / 2);            // simul_whisper.py:350 (unclamped: the policy's
+        content_out[i] = s.content_len;                             // frame_threshold test needs the true value)
         xkv[i] = s.cross_kv;
     }
     sg.upload();
 
     {   ProfScope ps(e, WLK_KC_MEL, 0, (double)n * (480000.0 * 4 + 3000.0 * nm * es));
-        mel_forward(mj_dev, n, nm, W.filtT, W.window, W.twiddle, W.filt_span, e->act, e->st); }
+        mel_forward(mj_dev, n, nm, W.filtT, W.window, W.twiddle, W.filt_span, e->act, max_frames, e->st); }
     run_encoder(e, sids, n, xkv_dev);
 }
 
@@ -470,7 +515,7 @@ void run_encoder(wlk_engine* e, const int32_t* sids, int n, void** xkv_dev) {
     // conv1 (k=3, pad=1) as a GEMM over overlapping rows of the time-major mel: row t = frames t-1..t+1
     {   GemmArgs g;
         g.A = e->mel_t; g.a_type = e->act; g.lda = nm;
-        g.W = W.Wc1; g.w_type = e->act; g.ldw = 3 * nm;
+        g.W = W.Wc1; g.w_type = e->wt; g.ldw = 3 * nm;
         g.M = n * MEL_ROWS - 2; g.N = d; g.K = 3 * nm;
         g.epi.bias = W.bc1; g.epi.gelu = 1;
         g.epi.C = offs(e->h1, (size_t)d, es); g.epi.c_type = e->act; g.epi.ldc = d;
@@ -479,7 +524,7 @@ void run_encoder(wlk_engine* e, const int32_t* sids, int n, void** xkv_dev) {
     // conv2 (k=3, stride 2, pad=1): row t = padded rows 2t..2t+2 -> pitch 2d, then GELU and + positional
     {   GemmArgs g;
         g.A = e->h1; g.a_type = e->act; g.lda = 2 * d;
-        g.W = W.Wc2; g.w_type = e->act; g.ldw = 3 * d;
+        g.W = W.Wc2; g.w_type = e->wt; g.ldw = 3 * d;
         g.M = n * (N_CTX + 1) - 1; g.N = d; g.K = 3 * d;
         g.epi.bias = W.bc2; g.epi.gelu = 1; g.epi.residual = W.enc_pos; g.epi.ldr = d;
         g.epi.mode = EPI_ROWPTR; g.epi.batch_ptrs = e->xptrs_dev; g.epi.rows_per_batch = N_CTX + 1;
@@ -493,7 +538,7 @@ void run_encoder(wlk_engine* e, const int32_t* sids, int n, void** xkv_dev) {
         {   ProfScope ps(e, WLK_KC_LN, 0, (double)M * d * (4 + es));
             layernorm(e->x, d, L.ln1w, L.ln1b, e->xn, e->act, d, M, d, nullptr, e->st); }
         {   GemmArgs g;
-            g.A = e->xn; g.a_type = e->act; g.lda = d; g.W = L.Wqkv; g.w_type = e->act; g.ldw = d;
+            g.A = e->xn; g.a_type = e->act; g.lda = d; g.W = L.Wqkv; g.w_type = e->wt; g.ldw = d;
             g.M = M; g.N = 3 * d; g.K = d;
             g.epi.bias = L.bqkv; g.epi.col_scale = qk_scale; g.epi.scale_cols = 2 * d;
             g.epi.C = e->qkv; g.epi.c_type = e->act; g.epi.ldc = 3 * d;
@@ -505,7 +550,7 @@ void run_encoder(wlk_engine* e, const int32_t* sids, int n, void** xkv_dev) {
             else
                 enc_attention_simt(e->qkv, e->act, n, D.n_audio_head, d, e->att, e->st); }
         {   GemmArgs g;
-            g.A = e->att; g.a_type = e->act; g.lda = d; g.W = L.Wo; g.w_type = e->act; g.ldw = d;
+            g.A = e->att; g.a_type = e->act; g.lda = d; g.W = L.Wo; g.w_type = e->wt; g.ldw = d;
             g.M = M; g.N = d; g.K = d;
             g.epi.bias = L.bo; g.epi.residual = e->x; g.epi.ldr = d;
             g.epi.C = e->x; g.epi.c_type = DT_F32; g.epi.ldc = d;
@@ -513,13 +558,13 @@ void run_encoder(wlk_engine* e, const int32_t* sids, int n, void** xkv_dev) {
         {   ProfScope ps(e, WLK_KC_LN, 0, (double)M * d * (4 + es));
             layernorm(e->x, d, L.ln2w, L.ln2b, e->xn, e->act, d, M, d, nullptr, e->st); }
         {   GemmArgs g;
-            g.A = e->xn; g.a_type = e->act; g.lda = d; g.W = L.W1; g.w_type = e->act; g.ldw = d;
+            g.A = e->xn; g.a_type = e->act; g.lda = d; g.W = L.W1; g.w_type = e->wt; g.ldw = d;
             g.M = M; g.N = 4 * d; g.K = d;
             g.epi.bias = L.b1; g.epi.gelu = 1;
             g.epi.C = e->hid; g.epi.c_type = e->act; g.epi.ldc = 4 * d;
             run_gemm(e, g, WLK_KC_GEMM_ENC); }
         {   GemmArgs g;
-            g.A = e->hid; g.a_type = e->act; g.lda = 4 * d; g.W = L.W2; g.w_type = e->act; g.ldw = 4 * d;
+            g.A = e->hid; g.a_type = e->act; g.lda = 4 * d; g.W = L.W2; g.w_type = e->wt; g.ldw = 4 * d;
             g.M = M; g.N = d; g.K = 4 * d;
             g.epi.bias = L.b2; g.epi.residual = e->x; g.epi.ldr = d;
             g.epi.C = e->x; g.epi.c_type = DT_F32; g.epi.ldc = d;
@@ -534,7 +579,7 @@ void run_encoder(wlk_engine* e, const int32_t* sids, int n, void** xkv_dev) {
     }
     // cross-attention K/V of every decoder layer in one GEMM, scattered head-major into each session
     {   GemmArgs g;
-        g.A = e->xn; g.a_type = e->act; g.lda = d; g.W = W.Wxkv; g.w_type = e->act; g.ldw = d;
+        g.A = e->xn; g.a_type = e->act; g.lda = d; g.W = W.Wxkv; g.w_type = e->wt; g.ldw = d;
         g.M = M; g.N = D.n_text_layer * 2 * dt; g.K = d;
         g.epi.bias = W.bxkv; g.epi.col_scale = qk_scale; g.epi.scale_cols = dt; g.epi.scale_period = 2 * dt;
         g.epi.mode = EPI_XKV; g.epi.batch_ptrs = xkv_dev; g.epi.rows_per_batch = N_CTX;
@@ -606,7 +651,7 @@ void decode_batch(wlk_engine* e, const int32_t* sids, int n, const int32_t* toke
         {   ProfScope ps(e, WLK_KC_LN);
             layernorm(e->dx, dt, L.ln1w, L.ln1b, e->dxn, e->act, dt, R, dt, nullptr, e->st); }
         {   GemmArgs g;
-            g.A = e->dxn; g.a_type = e->act; g.lda = dt; g.W = L.Wqkv; g.w_type = e->act; g.ldw = dt;
+            g.A = e->dxn; g.a_type = e->act; g.lda = dt; g.W = L.Wqkv; g.w_type = e->wt; g.ldw = dt;
             g.M = R; g.N = 3 * dt; g.K = dt;
             g.epi.bias = L.bqkv; g.epi.col_scale = qk_scale; g.epi.scale_cols = 2 * dt;
             g.epi.mode = EPI_SELF_QKV; g.epi.C = e->dq; g.epi.ldc = dt; g.epi.c_type = e->act;
@@ -616,14 +661,14 @@ void decode_batch(wlk_engine* e, const int32_t* sids, int n, const int32_t* toke
         {   ProfScope ps(e, WLK_KC_ATTN_DEC_SELF);
             dec_self_attention(e->dq, e->act, dj_dev, n, li, H, dt, ctx, e->datt, max_tq, e->st); }
         {   GemmArgs g;
-            g.A = e->datt; g.a_type = e->act; g.lda = dt; g.W = L.Wo; g.w_type = e->act; g.ldw = dt;
+            g.A = e->datt; g.a_type = e->act; g.lda = dt; g.W = L.Wo; g.w_type = e->wt; g.ldw = dt;
             g.M = R; g.N = dt; g.K = dt;
             g.epi.bias = L.bo; g.epi.residual = e->dx; g.epi.ldr = dt; g.epi.C = e->dx; g.epi.c_type = DT_F32; g.epi.ldc = dt;
             run_gemm(e, g, WLK_KC_GEMM_DEC); }
         {   ProfScope ps(e, WLK_KC_LN);
             layernorm(e->dx, dt, L.lncw, L.lncb, e->dxn, e->act, dt, R, dt, nullptr, e->st); }
         {   GemmArgs g;
-            g.A = e->dxn; g.a_type = e->act; g.lda = dt; g.W = L.Wqc; g.w_type = e->act; g.ldw = dt;
+            g.A = e->dxn; g.a_type = e->act; g.lda = dt; g.W = L.Wqc; g.w_type = e->wt; g.ldw = dt;
             g.M = R; g.N = dt; g.K = dt;
             g.epi.bias = L.bqc; g.epi.col_scale = qk_scale; g.epi.scale_cols = dt;
             g.epi.C = e->dq; g.epi.c_type = e->act; g.epi.ldc = dt;
@@ -635,19 +680,19 @@ void decode_batch(wlk_engine* e, const int32_t* sids, int n, const int32_t* toke
                                             e->datt, e->st);
             dec_cross_attention(e->dq, e->act, dj_dev, n, li, H, dt, ctx, e->align_rank_dev, e->datt, max_tq, tc_prefill, e->st); }
         {   GemmArgs g;
-            g.A = e->datt; g.a_type = e->act; g.lda = dt; g.W = L.Woc; g.w_type = e->act; g.ldw = dt;
+            g.A = e->datt; g.a_type = e->act; g.lda = dt; g.W = L.Woc; g.w_type = e->wt; g.ldw = dt;
             g.M = R; g.N = dt; g.K = dt;
             g.epi.bias = L.boc; g.epi.residual = e->dx; g.epi.ldr = dt; g.epi.C = e->dx; g.epi.c_type = DT_F32; g.epi.ldc = dt;
             run_gemm(e, g, WLK_KC_GEMM_DEC); }
         {   ProfScope ps(e, WLK_KC_LN);
             layernorm(e->dx, dt, L.ln2w, L.ln2b, e->dxn, e->act, dt, R, dt, nullptr, e->st); }
         {   GemmArgs g;
-            g.A = e->dxn; g.a_type = e->act; g.lda = dt; g.W = L.W1; g.w_type = e->act; g.ldw = dt;
+            g.A = e->dxn; g.a_type = e->act; g.lda = dt; g.W = L.W1; g.w_type = e->wt; g.ldw = dt;
             g.M = R; g.N = 4 * dt; g.K = dt;
             g.epi.bias = L.b1; g.epi.gelu = 1; g.epi.C = e->dhid; g.epi.c_type = e->act; g.epi.ldc = 4 * dt;
             run_gemm(e, g, WLK_KC_GEMM_DEC); }
         {   GemmArgs g;
-            g.A = e->dhid; g.a_type = e->act; g.lda = 4 * dt; g.W = L.W2; g.w_type = e->act; g.ldw = 4 * dt;
+            g.A = e->dhid; g.a_type = e->act; g.lda = 4 * dt; g.W = L.W2; g.w_type = e->wt; g.ldw = 4 * dt;
             g.M = R; g.N = dt; g.K = 4 * dt;
             g.epi.bias = L.b2; g.epi.residual = e->dx; g.epi.ldr = dt; g.epi.C = e->dx; g.epi.c_type = DT_F32; g.epi.ldc = dt;
             run_gemm(e, g, WLK_KC_GEMM_DEC); }
@@ -658,7 +703,7 @@ void decode_batch(wlk_engine* e, const int32_t* sids, int n, const int32_t* toke
         {   ProfScope ps(e, WLK_KC_LN);
             layernorm(e->dx, dt, W.lnw, W.lnb, e->dxn, e->act, dt, R, dt, nullptr, e->st); }
         GemmArgs g;
-        g.A = e->dxn; g.a_type = e->act; g.lda = dt; g.W = W.emb_act; g.w_type = e->act; g.ldw = dt;
+        g.A = e->dxn; g.a_type = e->act; g.lda = dt; g.W = W.emb_act; g.w_type = e->wt; g.ldw = dt;
         g.M = R; g.N = D.n_vocab; g.K = dt;
         g.epi.C = all_logits_dev; g.epi.c_type = DT_F32; g.epi.ldc = D.n_vocab;
         run_gemm(e, g, WLK_KC_LOGITS);
@@ -667,7 +712,7 @@ void decode_batch(wlk_engine* e, const int32_t* sids, int n, const int32_t* toke
     {   ProfScope ps(e, WLK_KC_LN);
         layernorm(e->dx, dt, W.lnw, W.lnb, e->dsel, e->act, dt, n_sel, dt, sel_dev, e->st); }
     {   GemmArgs g;
-        g.A = e->dsel; g.a_type = e->act; g.lda = dt; g.W = W.emb_act; g.w_type = e->act; g.ldw = dt;
+        g.A = e->dsel; g.a_type = e->act; g.lda = dt; g.W = W.emb_act; g.w_type = e->wt; g.ldw = dt;
         g.M = n_sel; g.N = D.n_vocab; g.K = dt;
         g.epi.mode = EPI_ROWPTR; g.epi.batch_ptrs = lptr_dev; g.epi.rows_per_batch = 1; g.epi.c_type = DT_F32;
         g.epi.ldc = D.n_vocab;
@@ -701,13 +746,19 @@ void decode_batch(wlk_engine* e, const int32_t* sids, int n, const int32_t* toke
                 cudaGraphExec_t exec = nullptr;
                 CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
                 cudaGraphDestroy(graph);
-                if (e->dec_graphs.size() >= 32) {                // batch sizes seen so far: bound the cache
-                    for (auto& kv : e->dec_graphs) cudaGraphExecDestroy(kv.second);
-                    e->dec_graphs.clear();
+                const size_t cap = (size_t)2 * e->cfg.max_batch + 8;   // (n, n_sel) pairs in use: n_sel is n or 2n
+                if (e->dec_graphs.size() >= cap) {               // evict the least recently used entry only
+                    auto lru = e->dec_graphs.begin();
+                    for (auto jt = e->dec_graphs.begin(); jt != e->dec_graphs.end(); ++jt)
+                        if (jt->second.last_use < lru->second.last_use) lru = jt;
+                    CUDA_CHECK(cudaStreamSynchronize(e->st));    // its last replay may still be in flight
+                    cudaGraphExecDestroy(lru->second.exec);
+                    e->dec_graphs.erase(lru);
                 }
-                it = e->dec_graphs.emplace(key, exec).first;
+                it = e->dec_graphs.emplace(key, wlk_engine::GraphSlot{exec, 0}).first;
             }
-            CUDA_CHECK(cudaGraphLaunch(it->second, e->st));
+            it->second.last_use = ++e->dec_graph_tick;
+            CUDA_CHECK(cudaGraphLaunch(it->second.exec, e->st));
         }
     }
     for (int i = 0; i < n; ++i) {
@@ -727,7 +778,8 @@ LogitJob make_logit_job(wlk_engine* e, Session& s, int window_iters, int full) {
     const int first = ni > window_iters ? ni - window_iters : 0;
     j.row_begin = ni ? s.iter_row_start[first] : 0;
     j.row_end = s.align_rows;
-    j.content_len = enc_owner(e, s).content_len;
+    // the reference slices a 1500-wide tensor ([:, :, :content_mel_len], simul_whisper.py:433): frames >= 1500 do not exist
+    j.content_len = std::min(enc_owner(e, s).content_len, N_CTX);
     j.full = full;
     return j;
 }
@@ -812,12 +864,17 @@ void create_engine(const wlk_dims* dims, const wlk_config* cfg, wlk_engine** out
     auto* e = new wlk_engine();
     e->dims = *dims; e->cfg = *cfg;
     e->num_sms = prop.multiProcessorCount;
+    WLK_CHECK(cfg->precision == WLK_PREC_FP32 || cfg->precision == WLK_PREC_BF16 || cfg->precision == WLK_PREC_BF16X3,
+              "unknown precision %d", cfg->precision);
     e->act = cfg->precision == WLK_PREC_BF16 ? DT_BF16 : DT_F32;
+    e->wt = cfg->precision == WLK_PREC_BF16X3 ? DT_BF16X2 : e->act;
     e->gemm_backend = cfg->gemm_backend != WLK_BACKEND_AUTO ? cfg->gemm_backend
                       : (e->act == DT_BF16 ? WLK_BACKEND_TCGEN05 : WLK_BACKEND_SIMT);
     e->attn_backend = cfg->attn_backend != WLK_BACKEND_AUTO ? cfg->attn_backend
                       : (e->act == DT_BF16 ? WLK_BACKEND_TCGEN05 : WLK_BACKEND_SIMT);
     if (e->act != DT_BF16) { e->gemm_backend = WLK_BACKEND_SIMT; e->attn_backend = WLK_BACKEND_SIMT; }
+    // BF16X3: fp32 activations and fp32 SIMT softmax / LayerNorm, every GEMM on the tensor cores with split operands
+    if (e->wt == DT_BF16X2) e->gemm_backend = WLK_BACKEND_TCGEN05;
     CUDA_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     {   const char* v = getenv("WLK_GRAPHS"); e->graphs_on = !(v && v[0] == '0'); }
     for (auto& t : e->timers) CUDA_CHECK(cudaEventCreate(&t));
@@ -855,6 +912,11 @@ void create_engine(const wlk_dims* dims, const wlk_config* cfg, wlk_engine** out
     e->hid = dmalloc_bytes((size_t)B * N_CTX * 4 * d * es, acct);
     e->audio_scratch = dmalloc<float>(e, AUDIO_CAP, acct);
     e->mel_scratch = dmalloc<float>(e, (size_t)MEL_ROWS * D.n_mels, acct);
+    if (e->gemm_backend == WLK_BACKEND_TCGEN05) {
+        e->sk_scratch = dmalloc<float>(e, SK_SCRATCH_FLOATS, acct);
+        e->sk_counters = dmalloc<int>(e, SK_MAX_TILES, acct);
+        CUDA_CHECK(cudaMemset(e->sk_counters, 0, SK_MAX_TILES * 4));
+    }
     {
         std::vector<int64_t> rows(2 * B);
         std::vector<void*> xp(B);
@@ -876,6 +938,13 @@ void create_engine(const wlk_dims* dims, const wlk_config* cfg, wlk_engine** out
     e->datt = dmalloc_bytes(R * dt * es, acct);
     e->dhid = dmalloc_bytes(R * 4 * dt * es, acct);
     e->dsel = dmalloc_bytes((size_t)2 * B * dt * es, acct);
+    if (e->wt == DT_BF16X2) {
+        size_t m = (size_t)B * N_CTX * 4 * d;                                  // fc2's operand (the MLP hidden)
+        m = std::max(m, R * 4 * dt);                                           // decoder MLP hidden
+        m = std::max(m, ((size_t)B * MEL_ROWS + 2) * (size_t)std::max(d, D.n_mels) + 3 * (size_t)d);   // conv views
+        e->a_split_elems = (m + 7) / 8 * 8;
+        e->a_split = dmalloc_bytes(e->a_split_elems * 2 * 2, acct);
+    }
     e->stg_bytes = (size_t)B * 1024 + R * 16 + 65536 + 1024 * 8;
     CUDA_CHECK(cudaMallocHost(&e->stg_host, e->stg_bytes));
     e->stg_dev = reinterpret_cast<uint8_t*>(dmalloc_bytes(e->stg_bytes, acct));
@@ -893,7 +962,7 @@ void destroy_engine(wlk_engine* e) {
     cudaStreamSynchronize(e->st);
     for (auto& s : e->sess) if (s.open && s.parent >= 0) free_session(e, s);     // forks before their parents
     for (auto& s : e->sess) if (s.open) free_session(e, s);
-    void* ptrs[] = {e->arena.base, e->stage_f32, e->mel_t, e->h1, e->x, e->xn, e->qkv, e->att, e->hid, e->audio_scratch, e->mel_scratch, e->beam_scratch,
+    void* ptrs[] = {e->arena.base, e->stage_f32, e->mel_t, e->h1, e->x, e->xn, e->qkv, e->att, e->hid, e->audio_scratch, e->mel_scratch, e->beam_scratch, e->sk_scratch, e->sk_counters, e->a_split,
                     e->pad_rows_dev, e->xptrs_dev, e->dx, e->dxn, e->dq, e->datt, e->dhid, e->dsel, e->stg_dev,
                     e->res_dev, e->align_rank_dev, e->kv_maps_dev, e->all_logits_dev};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -904,7 +973,7 @@ void destroy_engine(wlk_engine* e) {
     for (auto& p : e->prof) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto& p : e->ev_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (e->stg_done) cudaEventDestroy(e->stg_done);
-    for (auto& kv : e->dec_graphs) cudaGraphExecDestroy(kv.second);
+    for (auto& kv : e->dec_graphs) cudaGraphExecDestroy(kv.second.exec);
     cudaStreamDestroy(e->st);
     delete e;
 }
@@ -1003,7 +1072,8 @@ int wlk_engine_set_alignment_heads(wlk_engine* e, const int32_t* pairs, int n_pa
         e->align_rank_host[(size_t)l * e->dims.n_text_head + h] = i;
     }
     e->n_align = n_pairs;
-    for (auto& kv : e->dec_graphs) cudaGraphExecDestroy(kv.second);       // captured launches bake the head count in
+    CUDA_CHECK(cudaStreamSynchronize(e->st));
+    for (auto& kv : e->dec_graphs) cudaGraphExecDestroy(kv.second.exec);  // captured launches bake the head count in
     e->dec_graphs.clear(); e->dec_graph_seen.clear();
     CUDA_CHECK(cudaMemcpy(e->align_rank_dev, e->align_rank_host.data(), e->align_rank_host.size() * 4, cudaMemcpyHostToDevice));
     WLK_API_END
@@ -1323,12 +1393,12 @@ int wlk_read_mel(wlk_engine* e, int32_t sid, float* out) {
     MelJob* mj_dev; MelJob* mj = sg.host<MelJob>(1, &mj_dev);
     const int64_t N = s.audio_len;
     int64_t n_compute = (N + 199) / HOP + 1;
-    if (n_compute > N_FRAMES + 2) n_compute = N_FRAMES + 2;
+    if (n_compute > MEL_MAX_FRAMES) n_compute = MEL_MAX_FRAMES;
     float* scratch = e->mel_scratch;
     mj[0].audio = s.audio; mj[0].raw = s.mel_raw; mj[0].blockmax = s.mel_blockmax; mj[0].out = scratch;
     mj[0].n = (int32_t)N; mj[0].n_compute = (int32_t)n_compute; mj[0].n_total = (int32_t)((N + 480000) / HOP); mj[0].pad = 0;
     sg.upload();
-    mel_forward(mj_dev, 1, nm, e->w.filtT, e->w.window, e->w.twiddle, e->w.filt_span, DT_F32, e->st);
+    mel_forward(mj_dev, 1, nm, e->w.filtT, e->w.window, e->w.twiddle, e->w.filt_span, DT_F32, (int)n_compute, e->st);
     float* h = tap_buffer(e, (size_t)MEL_ROWS * nm);
     CUDA_CHECK(cudaMemcpyAsync(h, scratch, (size_t)MEL_ROWS * nm * 4, cudaMemcpyDeviceToHost, e->st));
     CUDA_CHECK(cudaStreamSynchronize(e->st));
@@ -1386,6 +1456,8 @@ int wlk_op_gemm(wlk_engine* e, int backend, const void* A, int a_type, int64_t l
     GemmArgs g;
     g.A = A; g.a_type = a_type; g.lda = lda; g.W = Wm; g.w_type = w_type; g.ldw = ldw; g.M = M; g.N = N; g.K = K;
     g.epi.bias = bias; g.epi.gelu = gelu & 1; g.epi.C = C; g.epi.c_type = c_type; g.epi.ldc = ldc;
+    g.sk_scratch = e->sk_scratch; g.sk_scratch_floats = SK_SCRATCH_FLOATS;
+    g.sk_counters = e->sk_counters; g.sk_max_tiles = SK_MAX_TILES;
     if (gelu & 2) { WLK_CHECK(c_type == DT_F32, "in-place accumulation needs an fp32 output"); g.epi.residual = (const float*)C; g.epi.ldr = ldc; }
     ProfScope ps(e, WLK_KC_MISC, 2.0 * M * (double)N * K, 0);
     if (backend == WLK_BACKEND_TCGEN05) gemm_tcgen05(g, e->st, e->num_sms, 0);

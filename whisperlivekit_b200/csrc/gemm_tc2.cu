@@ -23,11 +23,13 @@ constexpr int BM2 = 256;          // rows per cluster tile (128 per CTA)
 constexpr int BN2 = 256;          // columns per cluster tile (each CTA stages 128 rows of W)
 constexpr int BK2 = 64;
 constexpr int STAGES2 = 6;
+constexpr int STAGES2_X3 = 3;           // X3: four tiles per slab (A_hi, A_lo, W_hi, W_lo), see gemm_tc.cu
 constexpr int NUM_EPI_WARPS2 = 16;      // 4 per TMEM lane quadrant, each draining a quarter of the tile's columns
 constexpr int NUM_THREADS2 = 64 + 32 * NUM_EPI_WARPS2;
 constexpr uint32_t A_BYTES2 = 128 * BK2 * 2;     // 16 KB
 constexpr uint32_t B_BYTES2 = 128 * BK2 * 2;     // 16 KB
-constexpr uint32_t STG_OFF2 = STAGES2 * (A_BYTES2 + B_BYTES2);
+constexpr uint32_t STG_OFF2 = STAGES2 * (A_BYTES2 + B_BYTES2);      // == STAGES2_X3 * 2 * (A_BYTES2 + B_BYTES2)
+static_assert(STAGES2 == 2 * STAGES2_X3, "both instantiations share one smem layout");
 constexpr uint32_t STG_BYTES2 = NUM_EPI_WARPS2 * EPI_BIAS_FLOATS * 4;
 constexpr uint32_t BAR_OFF2 = STG_OFF2 + STG_BYTES2;
 constexpr uint32_t SMEM2 = BAR_OFF2 + (2 * STAGES2 + 4) * 8 + 16 + 1024;
@@ -83,14 +85,20 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on
         : "memory");
 }
 
+template <bool X3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M, int N, int K,
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmWlo, int M, int N, int K,
                 Epilogue epi) {
+    constexpr int NST = X3 ? STAGES2_X3 : STAGES2;
+    constexpr uint32_t STAGE_TX = (X3 ? 4u : 2u) * (A_BYTES2 + B_BYTES2);       // bytes landing on a full barrier (both CTAs)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
     const uint32_t sA = smem_base;
-    const uint32_t sB = smem_base + STAGES2 * A_BYTES2;
+    const uint32_t sB = smem_base + NST * A_BYTES2;
+    const uint32_t sAlo = sB + NST * B_BYTES2;                     // X3 only
+    const uint32_t sBlo = sAlo + NST * A_BYTES2;                   // X3 only
     const uint32_t bar_full = smem_base + BAR_OFF2;                // [STAGES2]  (used in the leader)
     const uint32_t bar_empty = bar_full + STAGES2 * 8;             // [STAGES2]  (each CTA its own)
     const uint32_t bar_tfull = bar_empty + STAGES2 * 8;            // [2]        (each CTA its own)
@@ -111,7 +119,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmW);
-        for (int i = 0; i < STAGES2; ++i) {
+        if (X3) { ptx::prefetch_tensormap(&tmAlo); ptx::prefetch_tensormap(&tmWlo); }
+        for (int i = 0; i < NST; ++i) {
             ptx::mbar_init(bar_full + 8 * i, 2);                   // one arrive per CTA's producer
             ptx::mbar_init(bar_empty + 8 * i, 1);                  // one multicast commit
         }
@@ -140,11 +149,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tile_coords(tile, num_m, num_n, band, &m_blk, &n_blk);
                 for (int kb = 0; kb < num_k; ++kb) {
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    if (leader) ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * (A_BYTES2 + B_BYTES2));
+                    if (leader) ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, STAGE_TX);
                     else mbar_arrive_cta(bar_full + 8 * stage, 0);
                     tma_load_2d_pair(sA + stage * A_BYTES2, &tmA, bar_full + 8 * stage, kb * BK2, m_blk * BM2 + rank * 128);
                     tma_load_2d_pair(sB + stage * B_BYTES2, &tmW, bar_full + 8 * stage, kb * BK2, n_blk * BN2 + rank * 128);
-                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                    if (X3) {
+                        tma_load_2d_pair(sAlo + stage * A_BYTES2, &tmAlo, bar_full + 8 * stage, kb * BK2, m_blk * BM2 + rank * 128);
+                        tma_load_2d_pair(sBlo + stage * B_BYTES2, &tmWlo, bar_full + 8 * stage, kb * BK2, n_blk * BN2 + rank * 128);
+                    }
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -163,14 +176,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (lane == 0) {
                         const uint64_t da = ptx::umma_desc_kmajor_sw128(sA + stage * A_BYTES2);
                         const uint64_t db = ptx::umma_desc_kmajor_sw128(sB + stage * B_BYTES2);
+                        const uint64_t dal = ptx::umma_desc_kmajor_sw128(sAlo + stage * A_BYTES2);
+                        const uint64_t dbl = ptx::umma_desc_kmajor_sw128(sBlo + stage * B_BYTES2);
 #pragma unroll
-                        for (int k = 0; k < BK2 / 16; ++k)
+                        for (int k = 0; k < BK2 / 16; ++k) {
                             umma_bf16_ss_pair(tmem_base + as * BN2, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            if (X3) {       // + A_lo W_hi + A_hi W_lo into the same accumulator
+                                umma_bf16_ss_pair(tmem_base + as * BN2, dal + 2 * k, db + 2 * k, idesc, 1u);
+                                umma_bf16_ss_pair(tmem_base + as * BN2, da + 2 * k, dbl + 2 * k, idesc, 1u);
+                            }
+                        }
                         umma_commit_pair(bar_empty + 8 * stage);
                         if (kb == num_k - 1) umma_commit_pair(bar_tfull + 8 * as);
                     }
                     __syncwarp();
-                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -204,19 +224,29 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 }  // namespace
 
-void gemm_tcgen05_pair(const GemmArgs& g, cudaStream_t st, int num_sms) {
-    CUtensorMap tmA, tmW;
+template <bool X3>
+static void launch_pair(const GemmArgs& g, const void* A_hi, const void* A_lo, cudaStream_t st, int num_sms) {
+    CUtensorMap tmA, tmW, tmAlo, tmWlo;
     std::string err;
-    WLK_CHECK(make_tmap_bf16_2d(&tmA, g.A, g.M, g.K, g.lda, 128, BK2, &err), "A tensor map: %s", err.c_str());
+    WLK_CHECK(make_tmap_bf16_2d(&tmA, A_hi, g.M, g.K, g.lda, 128, BK2, &err), "A tensor map: %s", err.c_str());
     WLK_CHECK(make_tmap_bf16_2d(&tmW, g.W, g.N, g.K, g.ldw, 128, BK2, &err), "W tensor map: %s", err.c_str());
+    if (X3) {
+        WLK_CHECK(make_tmap_bf16_2d(&tmAlo, A_lo, g.M, g.K, g.lda, 128, BK2, &err), "A_lo tensor map: %s", err.c_str());
+        WLK_CHECK(make_tmap_bf16_2d(&tmWlo, g.W_lo, g.N, g.K, g.ldw, 128, BK2, &err), "W_lo tensor map: %s", err.c_str());
+    } else { tmAlo = tmA; tmWlo = tmW; }
     static bool seen[64] = {};
     if (first_on_device(seen))
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2));
     const int num_tiles = ((g.M + BM2 - 1) / BM2) * ((g.N + BN2 - 1) / BN2);
     int clusters = num_sms / 2;
     if (num_tiles < clusters) clusters = num_tiles;
-    gemm_tc2_kernel<<<2 * clusters, NUM_THREADS2, SMEM2, st>>>(tmA, tmW, g.M, g.N, g.K, g.epi);
+    gemm_tc2_kernel<X3><<<2 * clusters, NUM_THREADS2, SMEM2, st>>>(tmA, tmW, tmAlo, tmWlo, g.M, g.N, g.K, g.epi);
     CUDA_CHECK(cudaGetLastError());
+}
+
+void gemm_tcgen05_pair(const GemmArgs& g, const void* A_hi, const void* A_lo, cudaStream_t st, int num_sms) {
+    if (g.w_type == DT_BF16X2) launch_pair<true>(g, A_hi, A_lo, st, num_sms);
+    else launch_pair<false>(g, A_hi, A_lo, st, num_sms);
 }
 
 }  // namespace wlk

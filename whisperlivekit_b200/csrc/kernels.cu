@@ -130,7 +130,7 @@ mel_power_kernel(const MelJob* __restrict__ jobs, int n_mels, const float* __res
         float acc = 0.f;
         for (int k = sp.x; k < sp.y; ++k) acc = fmaf(filtT[k * n_mels + m], pw[fr][k], acc);
         const float v = log10f(fmaxf(acc, 1e-10f));
-        job.raw[(int64_t)f * n_mels + m] = v;
+        if (f < MEL_STORE_FRAMES) job.raw[(int64_t)f * n_mels + m] = v;
         lmax = fmaxf(lmax, v);
     }
     // block max over 7 warps
@@ -150,10 +150,11 @@ mel_finalize_kernel(const MelJob* __restrict__ jobs, int n_mels) {
     __shared__ float red[8];
     const MelJob job = jobs[blockIdx.y];
     float m = -10.0f;    // frames inside the zero padding contribute log10(1e-10)
-    for (int i = threadIdx.x; i < MEL_MAX_CTAS; i += 256) m = fmaxf(m, job.blockmax[i]);
+    const int n_valid = min(job.n_compute, job.n_total);
+    const int n_ctas = (n_valid + MEL_FRAMES_PER_CTA - 1) / MEL_FRAMES_PER_CTA;
+    for (int i = threadIdx.x; i < n_ctas; i += 256) m = fmaxf(m, job.blockmax[i]);
     const float gmax = block_max_all<256>(m, red);
     const float thr = gmax - 8.0f;
-    const int n_valid = min(job.n_compute, job.n_total);
     TO* out = reinterpret_cast<TO*>(job.out);
     const int64_t total = (int64_t)MEL_ROWS * n_mels;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
@@ -169,8 +170,11 @@ mel_finalize_kernel(const MelJob* __restrict__ jobs, int n_mels) {
 }
 
 void mel_forward(const MelJob* jobs_dev, int batch, int n_mels, const float* filtT, const float* window,
-                 const float2* twiddle, const int2* filt_span, int out_type, cudaStream_t st) {
-    dim3 g1(MEL_MAX_CTAS, batch);
+                 const float2* twiddle, const int2* filt_span, int out_type, int max_frames, cudaStream_t st) {
+    int ctas = (max_frames + MEL_FRAMES_PER_CTA - 1) / MEL_FRAMES_PER_CTA;
+    if (ctas < 1) ctas = 1;
+    if (ctas > MEL_MAX_CTAS) ctas = MEL_MAX_CTAS;
+    dim3 g1(ctas, batch);
     mel_power_kernel<<<g1, 224, 0, st>>>(jobs_dev, n_mels, filtT, window, twiddle, filt_span);
     CUDA_CHECK(cudaGetLastError());
     dim3 g2(64, batch);
@@ -199,8 +203,11 @@ mel_window_finalize_kernel(const MelJob* __restrict__ jobs, const int2* __restri
 }
 void mel_window_forward(const MelJob* jobs_dev, const int2* ranges_dev, const int64_t* out_off_dev, float* out_dev, int batch,
                         int n_mels, const float* filtT, const float* window, const float2* twiddle, const int2* filt_span,
-                        cudaStream_t st) {
-    dim3 g1(MEL_MAX_CTAS, batch);
+                        int max_frames, cudaStream_t st) {
+    int ctas = (max_frames + MEL_FRAMES_PER_CTA - 1) / MEL_FRAMES_PER_CTA;
+    if (ctas < 1) ctas = 1;
+    if (ctas > MEL_MAX_CTAS) ctas = MEL_MAX_CTAS;
+    dim3 g1(ctas, batch);
     mel_power_kernel<<<g1, 224, 0, st>>>(jobs_dev, n_mels, filtT, window, twiddle, filt_span);
     CUDA_CHECK(cudaGetLastError());
     dim3 g2(8, batch);
@@ -276,6 +283,21 @@ void convert_to_f32(const void* src, int src_type, float* dst, int64_t n, cudaSt
     if (grid < 1) grid = 1;
     if (src_type == DT_F32) cvt_to_f32_kernel<float><<<grid, 256, 0, st>>>((const float*)src, dst, n);
     else cvt_to_f32_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)src, dst, n);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void split_planes_kernel(const float* __restrict__ s, bf16* __restrict__ hi, bf16* __restrict__ lo, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = s[i];
+        const bf16 h = __float2bfloat16_rn(x);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+}
+void split_f32_to_planes(const float* src, bf16* hi, bf16* lo, int64_t n, cudaStream_t st) {
+    int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+    if (grid < 1) grid = 1;
+    split_planes_kernel<<<grid, 256, 0, st>>>(src, hi, lo, n);
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -13,27 +13,32 @@ constexpr int N_FREQ = 201;
 constexpr int N_FFT = 400;
 constexpr int HOP = 160;
 constexpr int MEL_FRAMES_PER_CTA = 16;
-constexpr int MEL_MAX_CTAS = (N_FRAMES + 2 + MEL_FRAMES_PER_CTA - 1) / MEL_FRAMES_PER_CTA;   // 376
+constexpr int MEL_STORE_FRAMES = N_FRAMES + 2;          // rows of MelJob.raw
+constexpr int MEL_MAX_FRAMES = 2 * N_FRAMES + 2;        // a session may buffer up to 60 s: every frame joins the global max
+constexpr int MEL_MAX_CTAS = (MEL_MAX_FRAMES + MEL_FRAMES_PER_CTA - 1) / MEL_FRAMES_PER_CTA;   // 376
 
 struct MelJob {                 // one per session in the batch (device array)
     const float* audio;         // device, n samples
-    float* raw;                 // [MEL_ROWS-2 + 2][n_mels] fp32 log10(max(mel,1e-10)) for frames < n_compute
+    float* raw;                 // [MEL_STORE_FRAMES][n_mels] fp32 log10(max(mel,1e-10)) for frames < min(n_compute, MEL_STORE_FRAMES)
     float* blockmax;            // [MEL_MAX_CTAS]
     void* out;                  // [MEL_ROWS][n_mels] activation type, time-major, zero pad rows
     int32_t n;                  // samples
-    int32_t n_compute;          // frames whose window touches audio (others are the silence constant)
+    int32_t n_compute;          // frames whose window touches audio (others are the silence constant); frames past
+                                // MEL_STORE_FRAMES only feed the global maximum (audio.py:154-155 takes it over the whole
+                                // padded spectrogram, before pad_or_trim cuts it to 3000 frames)
     int32_t n_total;            // floor((n + 480000) / 160): frames the reference's STFT keeps
     int32_t pad;
 };
 
+// max_frames: the largest n_compute in the batch (sizes the grid)
 void mel_forward(const MelJob* jobs_dev, int batch, int n_mels, const float* filtT, const float* window,
-                 const float2* twiddle, const int2* filt_span, int out_type, cudaStream_t st);
+                 const float2* twiddle, const int2* filt_span, int out_type, int max_frames, cudaStream_t st);
 
 // streaming-window variant (Qwen3 front end): MelJob.pad = 1, n_compute = n_total = window frames; emits frames
 // [ranges[i].x, ranges[i].y) of job i as fp32 [frames][n_mels] at row out_off[i] of `out`
 void mel_window_forward(const MelJob* jobs_dev, const int2* ranges_dev, const int64_t* out_off_dev, float* out_dev, int batch,
                         int n_mels, const float* filtT, const float* window, const float2* twiddle, const int2* filt_span,
-                        cudaStream_t st);
+                        int max_frames, cudaStream_t st);
 
 void mel_import(const float* mel_dev /*[n_mels,3000]*/, void* out /*[3002,n_mels]*/, int out_type, int n_mels, cudaStream_t st);
 
@@ -100,6 +105,8 @@ void dtw_batch(const void* jobs_dev, int n_jobs, int max_tokens, cudaStream_t st
 
 void convert_f32_to(const float* src, void* dst, int dst_type, int64_t n, cudaStream_t st);
 void convert_to_f32(const void* src, int src_type, float* dst, int64_t n, cudaStream_t st);
+// WLK_PREC_BF16X3 weights: hi = bf16(x), lo = bf16(x - hi)
+void split_f32_to_planes(const float* src, bf16* hi, bf16* lo, int64_t n, cudaStream_t st);
 void pcm16_to_f32(const int16_t* src_dev, float* dst_dev, int64_t n, cudaStream_t st);
 // conv weight [c_out, c_in, 3] -> [c_out, 3 * c_in] (tap-major) in the destination type
 void pack_conv_weight(const float* w, void* dst, int dst_type, int c_out, int c_in, cudaStream_t st);

@@ -225,6 +225,7 @@ struct wlk_qwen {
     float *mel = nullptr, *x = nullptr, *posbuf = nullptr, *outbuf = nullptr;
     void *a1 = nullptr, *col = nullptr, *a2 = nullptr, *a3 = nullptr, *xn = nullptr, *qb = nullptr, *att = nullptr, *hid = nullptr;
     void *qkv_scratch = nullptr;
+    float* sk_scratch = nullptr; int* sk_counters = nullptr;      // this engine's split-K workspace (GemmArgs)
     uint8_t *stg_h = nullptr, *stg_d = nullptr; size_t stg_bytes = 0;
     size_t es() const { return dtype_size(act); }
 };
@@ -242,6 +243,8 @@ void* qalloc(wlk_qwen* q, size_t bytes, size_t* acct) {
 
 void qgemm(wlk_qwen* q, GemmArgs& g) {
     if (g.M <= 0) return;
+    g.sk_scratch = q->sk_scratch; g.sk_scratch_floats = SK_SCRATCH_FLOATS;
+    g.sk_counters = q->sk_counters; g.sk_max_tiles = SK_MAX_TILES;
     if (q->gemm_backend == WLK_BACKEND_TCGEN05 && gemm_tcgen05_supported(g, nullptr)) gemm_tcgen05(g, q->st, q->num_sms);
     else gemm_simt(g, q->st);
 }
@@ -443,6 +446,11 @@ void create(const wlk_qwen_dims* dims, const wlk_config* cfg, wlk_qwen** out) {
     q->twiddle = (float2*)qalloc(q, N_FFT * 8, aw);
     q->filt_span = (int2*)qalloc(q, (size_t)D.n_mels * 8, aw);
     q->audio_scratch = (float*)qalloc(q, (size_t)QMEL_AUDIO_CAP * 4, ws);
+    if (q->gemm_backend == WLK_BACKEND_TCGEN05) {
+        q->sk_scratch = (float*)qalloc(q, SK_SCRATCH_FLOATS * 4, ws);
+        q->sk_counters = (int*)qalloc(q, SK_MAX_TILES * 4, ws);
+        CUDA_CHECK(cudaMemset(q->sk_counters, 0, SK_MAX_TILES * 4));
+    }
     {   // periodic Hann window and DFT twiddles exp(-2 pi i t / 400), evaluated in double
         std::vector<float> win(N_FFT);
         std::vector<float2> tw(N_FFT);
@@ -711,9 +719,11 @@ void append_audio(wlk_qwen* q, const int32_t* sids, int n, const float* pcm, con
     MelJob* mj = reinterpret_cast<MelJob*>(q->stg_h + o_jobs);
     int2* rng = reinterpret_cast<int2*>(q->stg_h + o_rng);
     int64_t* ooff = reinterpret_cast<int64_t*>(q->stg_h + o_off);
+    int max_frames = 1;
     for (int k = 0; k < nj; ++k) {
         const int i = who[k];
         QSession& s = q->sess[sids[i]];
+        if (plan[i].frames > max_frames) max_frames = plan[i].frames;
         mj[k] = MelJob{s.audio, s.mel_raw, s.mel_blockmax, nullptr, (int32_t)s.buf_len, plan[i].frames, plan[i].frames, 1};
         rng[k] = make_int2(plan[i].first, plan[i].last);
         ooff[k] = frame_off[i];
@@ -721,7 +731,7 @@ void append_audio(wlk_qwen* q, const int32_t* sids, int n, const float* pcm, con
     CUDA_CHECK(cudaMemcpyAsync(q->stg_d, q->stg_h, off, cudaMemcpyHostToDevice, q->st));
     mel_window_forward(reinterpret_cast<const MelJob*>(q->stg_d + o_jobs), reinterpret_cast<const int2*>(q->stg_d + o_rng),
                        reinterpret_cast<const int64_t*>(q->stg_d + o_off), q->mel_out, nj, D.n_mels, q->filtT, q->window,
-                       q->twiddle, q->filt_span, q->st);
+                       q->twiddle, q->filt_span, max_frames, q->st);
     CUDA_CHECK(cudaMemcpyAsync(out, q->mel_out, (size_t)rows * D.n_mels * 4, cudaMemcpyDeviceToHost, q->st));
     // drop the samples no longer needed: keep MARGIN (8) frames of history before the next frame to emit (features.py:77-83)
     for (int k = 0; k < nj; ++k) {

@@ -43,7 +43,7 @@ class WhisperEngine:
         self.align_heads = [tuple(int(v) for v in h) for h in heads]
         be = {"auto": L.BACKEND_AUTO, "simt": L.BACKEND_SIMT, "tcgen05": L.BACKEND_TCGEN05}
         cdims = L.wlk_dims(*dims.as_tuple())
-        cfg = L.wlk_config(device=device, precision={"fp32": L.PREC_FP32, "bf16": L.PREC_BF16}[precision],
+        cfg = L.wlk_config(device=device, precision={"fp32": L.PREC_FP32, "bf16": L.PREC_BF16, "bf16x3": L.PREC_BF16X3}[precision],
                            max_sessions=max_sessions, max_batch=max_batch,
                            gemm_backend=be[gemm_backend], attn_backend=be[attn_backend],
                            max_align_heads=max(len(self.align_heads), 1), reserved=0)
