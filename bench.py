@@ -1,21 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- streaming Whisper large-v3, 0.5 s chunks, B concurrent streams per GPU.
+"""bench.py -- streaming Whisper on B200 behind WhisperLiveKit's AlignAtt seam.
+
+Headline config (`--config alignatt-large-v3`, the default; BASELINE.json's metric): Whisper large-v3, 0.5 s
+chunks, 30 s rolling window fully re-encoded per chunk (the reference's parity mode), B concurrent streams per GPU.
 
 One "step" = one 0.5 s tick of the hot path for every stream of the job, AlignAtt-style:
     append 0.5 s of PCM (host -> device) and drop the oldest 0.5 s of the full 30 s window,
     log-mel -> 32-layer encoder over all 1500 positions -> cross-K/V for 32 decoder layers,
     decoder prefill of a PREFIX-token prompt, then STEPS_PER_CHUNK greedy iterations of
     (suppress -> argmax/logprob -> alignment-head reduction -> most attended frame -> 1-token decode).
-That is the reference's per-chunk work in its parity (full re-encode) mode.
 
-Metric: realtime streams = audio seconds processed per wall second = B * 0.5 / step_time, i.e.
-how many concurrent streams the job sustains at RTF < 1; `rtf` is each stream's real-time factor
-when B streams share the GPU (step_time / 0.5 s), the reference's definition
-(scripts/run_scatter_benchmark.py:194-205).
+Numbers in the one JSON line:
+  value       audio seconds processed per wall second with the windows resident in HBM (scripted tick above,
+              CUDA events on the engine stream) = concurrent real-time streams the GPU sustains.
+  e2e         THROUGH THE SEAM, REAL-TIME PACED: B `StreamingAlignAtt` policies (the token-id mirror of
+              AlignAttBase.infer, whisperlivekit_b200/alignatt.py) on B caller threads over `BatchingEngine`, each
+              fed one 0.5 s host chunk every 0.5 s of wall clock at its own phase; the policy decides prefix and step
+              count; value = the largest probed B for which p95 latency (chunk arrival -> infer() returns) < 0.5 s
+              and the backlog does not grow.  Host->device chunk copies and device->host results are inside.
+  roofline    encoder GEMM class: algorithmic FLOPs / CUDA-event time inside the timed run vs the measured peak.
+  exact_mode  the same scripted tick in WLK_PREC_BF16X3 (1e-3-on-logits mode): the price of exactness.
+  other_configs  BASELINE configs 2, 3, 5 in brief (each also runnable as the main line with --config).
+  cpu_baseline / --impl reference: the STAGED UNMODIFIED reference (oracle/_ref: vendored torch Whisper behind its own
+              AlignAtt hooks) on the host cores, same per-chunk workload (oracle/ref_driver.py).
 
-    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--streams B] [--model large-v3]
-Multi-GPU: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...  (one rank per
-GPU; sessions are sharded, NCCL is used once to broadcast the packed weights; weak scaling).
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--config C] [--streams B] [--no-extras]
+Multi-GPU: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...  (one rank per GPU; sessions are
+sharded, NCCL is used once to broadcast the packed weights; weak scaling, no data-path collective).
 """
 from __future__ import annotations
 
@@ -37,6 +48,8 @@ CHUNK = 8000
 WINDOW = 480000
 PREFIX = 48
 STEPS_PER_CHUNK = 8
+UNIT = "concurrent real-time streams (audio-s per wall-s)"
+CONFIGS = ["alignatt-large-v3", "alignatt-base-en-1stream", "localagreement-large-v3-64", "qwen-tower-128"]
 
 
 def load_peaks():
@@ -82,23 +95,43 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port of the reference's CPU path on the host cores
+# reference arm / cpu_baseline: the staged, unmodified reference on the host cores (oracle/ref_driver.py)
 # ------------------------------------------------------------------------------------------
-def cpu_stream_chunk_seconds(dims, sd, heads, n_chunks=1, threads=None):
-    """Time `n_chunks` stream-chunk steps of the same workload on the CPU oracle (fp32 torch CPU ops,
-    the restatement of the reference's `--backend whisper` path).  Returns seconds per stream-chunk."""
-    import torch
+def reference_available() -> bool:
+    from oracle import stage_reference
+    return stage_reference.staged()
+
+
+def cpu_baseline_leg(dims, sd, heads, n_chunks=2):
+    """One stream, all host threads, `n_chunks` stream-chunks of the headline workload.  -> dict"""
+    from oracle import ref_driver as rd
+    cores = rd.host_cores()
+    if reference_available():
+        model = rd.build_model(dims, sd, heads)
+        per, threads = rd.time_single_stream(model, dims, PREFIX, STEPS_PER_CHUNK, n_chunks, cores, warmup=0)
+        kind, what = "reference", "staged unmodified reference (oracle/_ref): its AlignAtt hooks over its vendored torch Whisper, fp32"
+    else:                                                     # the recipe could not run (no /root/reference at build time)
+        import torch
+        torch.set_num_threads(cores)
+        per, threads = oracle_port_chunks(dims, sd, heads, n_chunks), torch.get_num_threads()
+        kind, what = "port", "oracle port of the reference CPU path (oracle/_ref not staged)"
+    sec = float(np.mean(per))
+    return dict(value=CHUNK_S / sec, unit=UNIT, cores=threads, kind=kind, cpu_model=rd.cpu_model(), nproc=os.cpu_count(),
+                sample=f"{n_chunks} stream-chunks of the same workload, 1 stream, {threads} threads; {what}",
+                seconds_per_stream_chunk=sec)
+
+
+def oracle_port_chunks(dims, sd, heads, n_chunks):
     from oracle import whisper_oracle as wo
     from whisperlivekit_b200.weights import synthetic_audio
-    if threads:
-        torch.set_num_threads(threads)
     eng = wo.OracleEngine(dims, sd, heads)
     sid = eng.open_session()
     eng.append_audio(sid, synthetic_audio(30.0, seed=1))
     prefix = list(eng.specials.sot_sequence_including_notimestamps()) + list(range(1000, 1000 + PREFIX - 4))
     sup = eng.specials.alignatt_suppress_tokens()
-    t0 = time.perf_counter()
+    per = []
     for c in range(n_chunks):
+        t0 = time.perf_counter()
         eng.drop_audio(sid, CHUNK)
         eng.append_audio(sid, synthetic_audio(CHUNK_S, seed=100 + c))
         eng.encode([sid])
@@ -107,18 +140,322 @@ def cpu_stream_chunk_seconds(dims, sd, heads, n_chunks=1, threads=None):
             eng.suppress([sid], sup)
             tok, _, _ = eng.greedy_and_align([sid])[0]
             eng.decode([sid], [[tok]])
-    return (time.perf_counter() - t0) / n_chunks, torch.get_num_threads()
+        per.append(time.perf_counter() - t0)
+    return per
 
 
+def reference_arm(args, dims, heads, metric, workload):
+    """bench.py --impl reference: rank 0 only.  Two figures: (ii) `cores` single-thread
+    streams in parallel, then (i) one stream on all cores; `value` is the better of the two (CPU throughput)."""
+    from oracle import ref_driver as rd
+    from whisperlivekit_b200.weights import synthetic_state_dict
+    import torch
+    torch.set_num_threads(1)                                  # nothing multi-threaded before the fork of figure (ii)
+    cores = rd.host_cores()
+    sd = synthetic_state_dict(dims, seed=0)
+    if not reference_available():
+        per = oracle_port_chunks(dims, sd, heads, 1)
+        torch.set_num_threads(cores)
+        per = oracle_port_chunks(dims, sd, heads, max(1, min(args.steps, 3)))
+        sec = float(np.mean(per))
+        base = dict(value=CHUNK_S / sec, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                    sample="oracle port (oracle/_ref not staged)")
+        fig_i, fig_ii = base, None
+    else:
+        model = rd.build_model(dims, sd, heads)
+        del sd
+        procs = cores
+        budget = float(os.environ.get("WLK_REF_PARALLEL_TIMEOUT", "240"))
+        wall, done = rd.time_parallel_single_thread(model, dims, PREFIX, STEPS_PER_CHUNK, procs, timeout_s=budget)
+        fig_ii = dict(procs=procs, finished=done, wall_s=wall,
+                      value=(done * CHUNK_S / wall) if done == procs else 0.0,
+                      note=("every process ran one stream-chunk at 1 thread" if done == procs else
+                            f"only {done}/{procs} single-thread stream-chunks finished within {budget:.0f} s: below "
+                            f"{procs * CHUNK_S / budget:.3f} streams"))
+        n = max(1, min(args.steps, 3))
+        per, threads = rd.time_single_stream(model, dims, PREFIX, STEPS_PER_CHUNK, n, cores, warmup=1)
+        sec = float(np.mean(per))
+        fig_i = dict(value=CHUNK_S / sec, unit=UNIT, cores=threads, kind="reference", seconds_per_stream_chunk=sec,
+                     sample=f"{n} stream-chunks, 1 stream on {threads} threads")
+    value = max(fig_i["value"], fig_ii["value"] if fig_ii else 0.0)
+    best = "one stream on all cores" if value == fig_i["value"] else f"{fig_ii['procs']} single-thread streams in parallel"
+    line = dict(metric=metric, value=value, unit=UNIT, n_gpus=args.gpus, steps=max(1, min(args.steps, 3)), warmup=1,
+                ms_per_step=CHUNK_S / value * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload=workload.replace(f"{args.streams} streams/GPU", "host CPU"), model=args.model,
+                            note="staged unmodified reference (oracle/_ref), `--backend whisper` path: its own AlignAtt hooks over "
+                                 "its vendored torch Whisper, fp32, scripted to the same per-chunk work as the B200 arm"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=fig_i.get("kind", "reference"),
+                                  cpu_model=rd.cpu_model(), nproc=os.cpu_count(), omp_env=os.environ.get("OMP_NUM_THREADS"),
+                                  sample=f"better of two figures ({best}); each step is one stream-chunk of the workload",
+                                  one_stream_all_cores=fig_i, parallel_single_thread=fig_ii),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# through-the-seam, real-time paced load (e2e)
+# ------------------------------------------------------------------------------------------
+def seam_probe(eng, B, n_ticks, warm_ticks, rng, phase_mode="staggered", context_tokens=300):
+    """B StreamingAlignAtt policies on B threads over a BatchingEngine, one 0.5 s chunk per stream per 0.5 s of wall
+    clock.  Every policy starts mid-conversation: a full 30 s window, ~4 hypothesis tokens per second of window and
+    `context_tokens` of left context (a long stream saturates the reference's context at n_text_ctx - 20 tokens,
+    align_att_base.py:100-113).  -> dict(pass, p50/p95/max latency, lag, policy statistics)"""
+    from whisperlivekit_b200.alignatt import AlignAttConfig, StreamingAlignAtt
+    from whisperlivekit_b200.batching import BatchingEngine
+    from whisperlivekit_b200.weights import synthetic_audio
+    beng = BatchingEngine(eng, max_batch=eng.max_batch, max_wait_s=0.004)
+    base = synthetic_audio(36.0, seed=7)
+    pols = []
+    for i in range(B):
+        p = StreamingAlignAtt(beng, AlignAttConfig(nonspeech_prob=1.01))     # the no-speech exit would hide the decode loop on random weights
+        off = int(rng.integers(0, 16000 * 5))
+        win = base[off: off + WINDOW]
+        p.segments = [CHUNK] * (WINDOW // CHUNK)
+        eng.append_audio(p.sid, win)
+        p.tokens = [list(p.initial_tokens)] + [[int(t) for t in rng.integers(1000, 40000, 2)] for _ in range(WINDOW // CHUNK - 1)]
+        p.context = [int(t) for t in rng.integers(1000, 40000, context_tokens)]
+        pols.append(p)
+    chunks = (0.05 * rng.standard_normal((8, CHUNK))).astype(np.float32)
+    phases = (np.arange(B) / B * CHUNK_S) if phase_mode == "staggered" else np.zeros(B)
+    total = warm_ticks + n_ticks
+    lat = np.zeros((B, total)); lag = np.zeros((B, total))
+    stats = dict(prefix=[], iters=[], stops={})
+    slock = threading.Lock()
+    errors = []
+    t_start = time.perf_counter() + 0.3
+
+    def worker(i):
+        p, ph = pols[i], phases[i]
+        try:
+            for k in range(total):
+                due = t_start + ph + k * CHUNK_S
+                now = time.perf_counter()
+                if now < due:
+                    time.sleep(due - now)
+                t0 = time.perf_counter()
+                p.insert_audio(chunks[(i + k) % 8])                      # H2D of the chunk + window slide
+                tr = p.infer()
+                t1 = time.perf_counter()
+                lat[i, k] = t1 - due
+                lag[i, k] = t0 - due
+                if k >= warm_ticks:
+                    with slock:
+                        stats["prefix"].append(tr.prefix_len); stats["iters"].append(len(tr.step_tokens))
+                        stats["stops"][tr.stop] = stats["stops"].get(tr.stop, 0) + 1
+        except Exception as e:                                           # noqa: BLE001
+            errors.append(repr(e))
+
+    th = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(B)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    wall = time.perf_counter() - t_start
+    bst = beng.stats
+    for p in pols:
+        p.close()
+    beng.close()
+    L = lat[:, warm_ticks:].reshape(-1)
+    G = lag[:, warm_ticks:]
+    third = max(1, n_ticks // 3)
+    lag_first, lag_last = float(G[:, :third].mean()), float(G[:, -third:].mean())
+    p95 = float(np.percentile(L, 95))
+    ok = (not errors) and p95 < CHUNK_S and lag_last < 0.1 + lag_first and float(G[:, -1].max()) < CHUNK_S
+    return dict(streams=B, ok=bool(ok), phase=phase_mode, ticks=n_ticks, p50_latency_s=float(np.percentile(L, 50)),
+                p95_latency_s=p95, max_latency_s=float(L.max()), start_lag_first_third_s=lag_first,
+                start_lag_last_third_s=lag_last, wall_s=wall, errors=errors[:3],
+                mean_prefix_tokens=float(np.mean(stats["prefix"])) if stats["prefix"] else 0.0,
+                mean_decode_iterations=float(np.mean(stats["iters"])) if stats["iters"] else 0.0, stops=stats["stops"],
+                engine_calls=bst["calls"], mean_sessions_per_call=bst["sessions"] / max(1, bst["calls"]),
+                max_sessions_in_call=bst["max_sessions_in_call"])
+
+
+def seam_search(eng, B0, Bmax, world, rng, n_ticks, warm_ticks):
+    """Probe B0, then walk up (pass) or down (fail) in steps of 16: at most three probes.  All ranks probe the same B
+    at the same time and a probe passes only if it passes on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    def probe(B):
+        if world > 1:
+            dist.barrier()
+        r = seam_probe(eng, B, n_ticks, warm_ticks, rng)
+        ok = r["ok"]
+        if world > 1:
+            t = torch.tensor([1 if ok else 0], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = bool(t.item())
+        r["ok_all_ranks"] = ok
+        return r
+
+    probes = [probe(B0)]
+    step = 16
+    if probes[0]["ok_all_ranks"]:
+        B = B0
+        while len(probes) < 3 and B + step <= Bmax:
+            r = probe(B + step)
+            probes.append(r)
+            if not r["ok_all_ranks"]:
+                break
+            B += step
+    else:
+        B = B0
+        while len(probes) < 3 and B - step >= step:
+            B -= step
+            r = probe(B)
+            probes.append(r)
+            if r["ok_all_ranks"]:
+                break
+    passed = [p for p in probes if p["ok_all_ranks"]]
+    best = max(passed, key=lambda p: p["streams"]) if passed else None
+    return best, probes
+
+
+# ------------------------------------------------------------------------------------------
+# the other BASELINE configs, in brief (each is also a main line with --config)
+# ------------------------------------------------------------------------------------------
+def config_base_en_single_stream(device=0, chunks=24):
+    """Config 2: whisper base.en, AlignAtt, 0.5 s chunks, ONE stream: per-chunk latency through StreamingAlignAtt
+    (host chunk in, tokens out), 10 s of audio growing to 22 s."""
+    from whisperlivekit_b200.alignatt import AlignAttConfig, StreamingAlignAtt
+    from whisperlivekit_b200.dims import ALIGNMENT_HEADS, DIMS
+    from whisperlivekit_b200.engine import WhisperEngine
+    from whisperlivekit_b200.weights import synthetic_audio, synthetic_state_dict
+    dims = DIMS["base.en"]
+    eng = WhisperEngine(dims, synthetic_state_dict(dims, seed=0), ALIGNMENT_HEADS["base.en"], precision="bf16", device=device,
+                        max_sessions=1, max_batch=1)
+    pol = StreamingAlignAtt(eng, AlignAttConfig(nonspeech_prob=1.01))
+    audio = synthetic_audio(10.0 + chunks * CHUNK_S, seed=5)
+    pol.segments = [CHUNK] * 20
+    eng.append_audio(pol.sid, audio[: 20 * CHUNK])
+    lat, iters = [], []
+    for k in range(chunks + 4):
+        seg = audio[(20 + k) * CHUNK: (21 + k) * CHUNK]
+        t0 = time.perf_counter()
+        pol.insert_audio(seg)
+        tr = pol.infer()
+        if k >= 4:
+            lat.append(time.perf_counter() - t0); iters.append(len(tr.step_tokens))
+    pol.close(); eng.close()
+    lat = np.asarray(lat) * 1e3
+    return dict(workload="whisper base.en AlignAtt greedy, 0.5 s chunks, 1 stream, host chunk in / tokens out per call",
+                metric="ms per 0.5 s chunk (process_iter latency)", ms_p50=float(np.percentile(lat, 50)),
+                ms_p95=float(np.percentile(lat, 95)), rtf=float(lat.mean() / 1e3 / CHUNK_S),
+                mean_decode_iterations=float(np.mean(iters)), chunks=chunks)
+
+
+def config_localagreement_64(device=0, streams=64, ticks=3, eng=None):
+    """Config 3: large-v3, LocalAgreement shape of work, 1.0 s chunks, 64 ragged streams (5-15 s buffers): per tick and
+    stream the audio buffer is encoded (device log-mel + encoder + cross-K/V), a 32-token hypothesis is decoded greedily
+    (batched over the streams), then the word-timestamp pass runs (all-position logits + alignment rows, no second
+    encode: SURVEY.md 8f-2).  Scripted over the engine entry points the LocalAgreement shim uses."""
+    from whisperlivekit_b200.dims import ALIGNMENT_HEADS, DIMS
+    from whisperlivekit_b200.engine import WhisperEngine
+    from whisperlivekit_b200.weights import synthetic_audio, synthetic_state_dict
+    dims = DIMS["large-v3"]
+    own = eng is None
+    if own:
+        eng = WhisperEngine(dims, synthetic_state_dict(dims, seed=0), ALIGNMENT_HEADS["large-v3"], precision="bf16", device=device,
+                            max_sessions=streams, max_batch=streams)
+    sp = eng.specials
+    rng = np.random.default_rng(3)
+    base = synthetic_audio(20.0, seed=11)
+    sids = [eng.open_session() for _ in range(streams)]
+    for s in sids:
+        eng.append_audio(s, base[: int(rng.integers(5, 15)) * 16000])
+    prompt = list(sp.sot_sequence_including_notimestamps())
+    sup = sp.alignatt_suppress_tokens()
+    per = []
+    for k in range(ticks + 1):
+        t0 = time.perf_counter()
+        for s in sids:
+            eng.drop_audio(s, 16000); eng.append_audio(s, base[:16000])          # 1.0 s chunk in, buffer trimmed by 1.0 s
+        eng.encode(sids)
+        eng.decode(sids, [prompt] * streams)
+        toks = [list(prompt) for _ in sids]
+        for _ in range(32):
+            eng.suppress(sids, sup)
+            r = eng.greedy_and_align(sids)
+            for i, t in enumerate(r):
+                toks[i].append(t[0])
+            eng.decode(sids, [[t[0]] for t in r])
+        for i, s in enumerate(sids):                                              # word-timestamp pass per stream
+            eng.reset_decoder(s)
+            eng.decode_all_logits(s, toks[i], sot_index=0)
+        eng.sync()
+        if k >= 1:
+            per.append(time.perf_counter() - t0)
+    for s in sids:
+        eng.close_session(s)
+    if own:
+        eng.close()
+    sec = float(np.mean(per))
+    return dict(workload=f"whisper large-v3, LocalAgreement-shaped tick, 1.0 s chunks, {streams} ragged streams (5-15 s buffers), "
+                         "32-token greedy hypothesis + word-timestamp pass per stream-tick",
+                metric=UNIT, value=streams * 1.0 / sec, ms_per_tick=sec * 1e3, rtf_per_stream=sec / 1.0, streams=streams)
+
+
+def config_qwen_tower(device=0, streams=128, ticks=24):
+    """Config 5: Qwen3-ASR-0.6B causal audio tower, 0.25 s chunks (raw audio in, device log-mel), encoder fires per
+    192-frame block, `streams` streams with staggered block phases."""
+    from whisperlivekit_b200.qwen_dims import QWEN_DIMS, synthetic_tower_state_dict
+    from whisperlivekit_b200.qwen_engine import QwenTowerEngine
+    from whisperlivekit_b200.weights import synthetic_audio
+    dims = QWEN_DIMS["qwen3-asr-0.6b"]
+    eng = QwenTowerEngine(dims, synthetic_tower_state_dict(dims, seed=0), precision="bf16", device=device,
+                          max_sessions=streams, max_batch=streams)
+    eng.load_mel_filters()
+    sids = [eng.open_session() for _ in range(streams)]
+    rng = np.random.default_rng(0)
+    pcm = synthetic_audio(40.0, seed=3)
+    mel = np.clip(0.3 + rng.standard_normal((256, dims.n_mels)).astype(np.float32), -1, 1.5)
+    eng.forward_chunk(sids, [mel[: int(p)] for p in rng.integers(0, 192, streams)])
+
+    def tick(k):
+        chunks = [pcm[(4000 * k + 997 * i) % 500000: (4000 * k + 997 * i) % 500000 + 4000] for i in range(streams)]
+        return eng.forward_chunk(sids, eng.mel_append(sids, chunks))
+
+    for k in range(8):
+        tick(k)
+    per, rows = [], 0
+    for k in range(ticks):
+        t0 = time.perf_counter()
+        out = tick(8 + k)
+        per.append(time.perf_counter() - t0)
+        rows += sum(o.shape[0] for o in out)
+    eng.close()
+    per = np.asarray(per)
+    return dict(workload=f"qwen3-asr-0.6b causal audio tower, 0.25 s chunks, raw audio in (device log-mel), {streams} streams, "
+                         "host audio in / encoder rows out per call (e2e by construction)",
+                metric=UNIT, value=float(streams * 0.25 / per.mean()), ms_per_tick_mean=float(per.mean() * 1e3),
+                ms_per_tick_p95=float(np.percentile(per, 95) * 1e3), encoder_steps=int(rows), streams=streams)
+
+
+def run_side_config(name, device):
+    fn = {"alignatt-base-en-1stream": config_base_en_single_stream, "localagreement-large-v3-64": config_localagreement_64,
+          "qwen-tower-128": config_qwen_tower}[name]
+    try:
+        return fn(device)
+    except Exception as e:                                                # noqa: BLE001
+        return dict(error=repr(e))
+
+
+# ------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="alignatt-large-v3", choices=CONFIGS)
     ap.add_argument("--streams", type=int, default=int(os.environ.get("WLK_BENCH_STREAMS", "96")), help="streams per GPU")
     ap.add_argument("--model", default="large-v3")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip exact_mode and other_configs")
+    ap.add_argument("--no-seam", action="store_true", help="skip the real-time paced run through the seam")
+    ap.add_argument("--seam-ticks", type=int, default=16)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -134,34 +471,33 @@ def main():
     workload = (f"whisper {args.model} AlignAtt greedy, {CHUNK_S}s chunks, 30 s rolling window fully re-encoded per chunk, "
                 f"{PREFIX}-token prefill + {STEPS_PER_CHUNK} decode steps per chunk, {args.streams} streams/GPU")
     metric = "realtime_streams_large_v3_0.5s_chunks"
-    unit = "concurrent real-time streams (audio-s per wall-s)"
 
-    # ---------------------------------------------------------------- reference arm (CPU)
+    # ---------------------------------------------------------------- reference arm (CPU), rank 0 only
     if args.impl == "reference":
         if rank != 0:
             return
-        sd = synthetic_state_dict(dims, seed=0)
-        for _ in range(1):                                   # one untimed warm-up stream-chunk
-            cpu_stream_chunk_seconds(dims, sd, heads, 1)
-        per = []
-        for _ in range(max(1, min(args.steps, 3))):          # bounded: each step = ONE stream-chunk
-            s, threads = cpu_stream_chunk_seconds(dims, sd, heads, 1)
-            per.append(s)
-        sec = float(np.mean(per))
-        value = CHUNK_S / sec
-        line = dict(metric=metric, value=value, unit=unit, n_gpus=args.gpus, steps=len(per), warmup=1,
-                    ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                    data="synthetic", impl="reference",
-                    config=dict(workload=workload.replace(f"{args.streams} streams/GPU", "1 stream on the host CPU"),
-                                model=args.model, note="oracle port of the reference CPU path (vendored torch Whisper, fp32); "
-                                "the reference itself cannot travel to the GPU box"),
-                    cpu_baseline=dict(value=value, unit=unit, cores=threads, kind="port",
-                                      sample=f"{len(per)} stream-chunk steps of the same workload, all host threads"),
-                    e2e=dict(value=value, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-        print(json.dumps(line))
+        reference_arm(args, dims, heads, metric, workload)
         return
 
-    # ---------------------------------------------------------------- B200 arm
+    # ---------------------------------------------------------------- side configs as the main line
+    if args.config != "alignatt-large-v3":
+        import torch
+        torch.cuda.set_device(local_rank)
+        if rank != 0:
+            return
+        sampler = ClockSampler(local_rank); sampler.start()
+        r = run_side_config(args.config, local_rank)
+        clocks = sampler.summary()
+        hib = args.config != "alignatt-base-en-1stream"
+        print(json.dumps(dict(metric=r.get("metric"), value=r.get("value", r.get("ms_p50")), unit=r.get("metric"), n_gpus=1,
+                              steps=args.steps, warmup=args.warmup, higher_is_better=hib, scaling="weak", vs_baseline=None,
+                              dtype="bf16", data="synthetic", config=dict(workload=r.get("workload"), name=args.config),
+                              e2e=dict(value=r.get("value", r.get("ms_p50")), unit=r.get("metric"),
+                                       note="these configs are timed through the host-buffer API: chunk H2D and result D2H are inside"),
+                              clocks=clocks, detail=r)))
+        return
+
+    # ---------------------------------------------------------------- B200 arm, headline config
     import torch
     import torch.distributed as dist
     from whisperlivekit_b200.engine import WhisperEngine
@@ -170,155 +506,225 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = args.streams
-    eng = WhisperEngine(dims, None, heads, precision="bf16", device=local_rank, max_sessions=B, max_batch=B,
-                        attn_backend=os.environ.get("WLK_ATTN", "auto"))
-    if rank == 0:
-        sd = synthetic_state_dict(dims, seed=0)
-        eng.load_state_dict(sd)
-    if world > 1:                                            # NCCL: weight broadcast at init, nothing else
-        ptr, nbytes = eng.weight_blob()
+    seam_bmax = 0 if args.no_seam else B + 32
+    sd = synthetic_state_dict(dims, seed=0) if rank == 0 else None
 
-        class _Blob:
-            __cuda_array_interface__ = dict(shape=(nbytes,), typestr="|u1", data=(ptr, False), version=2)
-        blob = torch.as_tensor(_Blob(), device=f"cuda:{local_rank}")
-        broadcast_blob(blob, src=0)
-        torch.cuda.synchronize()
-        if rank != 0:
-            eng.adopt_weights()
-    sp = eng.specials
-    sids = [eng.open_session() for _ in range(B)]
+    def make_engine(precision, max_sessions, max_batch):
+        eng = WhisperEngine(dims, None, heads, precision=precision, device=local_rank, max_sessions=max_sessions,
+                            max_batch=max_batch, attn_backend=os.environ.get("WLK_ATTN", "auto"))
+        if rank == 0:
+            eng.load_state_dict(sd)
+        if world > 1:                                        # NCCL: weight broadcast at init, nothing else
+            ptr, nbytes = eng.weight_blob()
+
+            class _Blob:
+                __cuda_array_interface__ = dict(shape=(nbytes,), typestr="|u1", data=(ptr, False), version=2)
+            blob = torch.as_tensor(_Blob(), device=f"cuda:{local_rank}")
+            broadcast_blob(blob, src=0)
+            torch.cuda.synchronize()
+            if rank != 0:
+                eng.adopt_weights()
+        return eng
+
     rng = np.random.default_rng(1000 + rank)
     base = synthetic_audio(36.0, seed=7)
-    for i, s in enumerate(sids):
-        off = int(rng.integers(0, 16000 * 5))
-        eng.append_audio(s, base[off: off + WINDOW] + 0.001 * rng.standard_normal(WINDOW).astype(np.float32))
-    prefix = list(sp.sot_sequence_including_notimestamps()) + list(range(1000, 1000 + PREFIX - 4))
-    sup = sp.alignatt_suppress_tokens()
-    chunk_host = torch.empty(B, CHUNK, dtype=torch.float32).pin_memory()
-    h2d = B * CHUNK * 4
-    d2h = B * 16 * (STEPS_PER_CHUNK + 1)                     # StepResult per stream per sync
 
-    host = dict(encode=0.0, prefill=0.0, step=0.0, n=0)      # host-side enqueue time of the engine calls (no sync inside)
+    def scripted(eng, B, steps, warmup, profile_pass=True):
+        """The scripted tick (module docstring).  -> (ms device-resident, ms with per-chunk IO, profile, host enqueue)"""
+        sp = eng.specials
+        sids = [eng.open_session() for _ in range(B)]
+        for s in sids:
+            off = int(rng.integers(0, 16000 * 5))
+            eng.append_audio(s, base[off: off + WINDOW] + 0.001 * rng.standard_normal(WINDOW).astype(np.float32))
+        prefix = list(sp.sot_sequence_including_notimestamps()) + list(range(1000, 1000 + PREFIX - 4))
+        sup = sp.alignatt_suppress_tokens()
+        chunk_host = torch.empty(B, CHUNK, dtype=torch.float32).pin_memory()
+        host = dict(encode=0.0, prefill=0.0, prefill_synced=0.0, step=0.0, n=0, ns=0)
 
-    def step(with_io: bool, k: int):
-        if with_io:
-            chunk_host.copy_(torch.from_numpy(0.05 * rng.standard_normal((B, CHUNK)).astype(np.float32)))
-            cn = chunk_host.numpy()
-            for i, s in enumerate(sids):
-                eng.drop_audio(s, CHUNK)
-                eng.append_audio(s, cn[i])
-        t0 = time.perf_counter()
-        eng.encode(sids)
-        t1 = time.perf_counter()
-        eng.decode(sids, [prefix] * B)
-        t2 = time.perf_counter()
-        host["encode"] += t1 - t0; host["prefill"] += t2 - t1; host["n"] += 1
-        eng.no_speech_prob(sids)
-        for _ in range(STEPS_PER_CHUNK):
-            eng.suppress(sids, sup)
-            r = eng.greedy_and_align(sids)
-            t3 = time.perf_counter()
-            eng.decode(sids, [[t[0]] for t in r])
-            host["step"] += time.perf_counter() - t3
+        def step(with_io, sync_before_prefill=False):
+            if with_io:
+                chunk_host.copy_(torch.from_numpy(0.05 * rng.standard_normal((B, CHUNK)).astype(np.float32)))
+                cn = chunk_host.numpy()
+                for i, s in enumerate(sids):
+                    eng.drop_audio(s, CHUNK)
+                    eng.append_audio(s, cn[i])
+            t0 = time.perf_counter()
+            eng.encode(sids)
+            t1 = time.perf_counter()
+            if sync_before_prefill:
+                eng.sync()
+                t1 = time.perf_counter()
+            eng.decode(sids, [prefix] * B)
+            t2 = time.perf_counter()
+            if sync_before_prefill:
+                host["prefill_synced"] += t2 - t1; host["ns"] += 1
+            else:
+                host["encode"] += t1 - t0; host["prefill"] += t2 - t1; host["n"] += 1
+            eng.no_speech_prob(sids)
+            for _ in range(STEPS_PER_CHUNK):
+                eng.suppress(sids, sup)
+                r = eng.greedy_and_align(sids)
+                t3 = time.perf_counter()
+                eng.decode(sids, [[t[0]] for t in r])
+                if not sync_before_prefill:
+                    host["step"] += time.perf_counter() - t3
 
-    def timed(with_io: bool, steps: int, warmup: int, profile: bool):
-        for k in range(warmup):
-            step(with_io, k)
-        eng.sync()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        if profile:
-            eng.profile_reset(); eng.profile_enable(True)
-        eng.timer_record(0)
-        for k in range(steps):
-            step(with_io, k)
-        eng.timer_record(1)
-        eng.sync()
-        ms = eng.timer_elapsed_ms(0, 1)
-        prof = eng.profile_read() if profile else None
-        eng.profile_enable(False)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            dist.barrier()
-        return ms, prof
+        def timed(with_io, steps, warmup, profile):
+            for _ in range(warmup):
+                step(with_io)
+            eng.sync()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            if profile:
+                eng.profile_reset(); eng.profile_enable(True)
+            eng.timer_record(0)
+            for _ in range(steps):
+                step(with_io)
+            eng.timer_record(1)
+            eng.sync()
+            ms = eng.timer_elapsed_ms(0, 1)
+            prof = eng.profile_read() if profile else None
+            eng.profile_enable(False)
+            if world > 1:
+                t = torch.tensor([ms], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+                dist.barrier()
+            return ms, prof
 
-    if os.environ.get("WLK_NCU"):
-        # profiler capture mode: warm up, then exactly one step between cudaProfilerStart/Stop
-        # (ncu --profile-from-start off ...).  Numbers printed under a profiler are never bench values.
-        for k in range(args.warmup):
-            step(False, k)
-        eng.sync()
-        torch.cuda.profiler.start()
-        step(False, 0)
-        eng.sync()
-        torch.cuda.profiler.stop()
-        print(json.dumps(dict(ncu_capture=True, streams=B)))
-        return
+        if os.environ.get("WLK_NCU"):
+            # profiler capture mode: warm up, then exactly one step between cudaProfilerStart/Stop
+            # (ncu --profile-from-start off ...).  Numbers printed under a profiler are never bench values.
+            for _ in range(warmup):
+                step(False)
+            eng.sync()
+            torch.cuda.profiler.start()
+            step(False)
+            eng.sync()
+            torch.cuda.profiler.stop()
+            print(json.dumps(dict(ncu_capture=True, streams=B)))
+            sys.exit(0)
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    ms_dev, _ = timed(False, args.steps, args.warmup, False)
-    clocks = sampler.summary() if sampler else None
-    ms_e2e, _ = timed(True, args.steps, max(1, args.warmup // 3), False)
-    # same steps once more with a CUDA-event pair around every kernel class launch (engine stream):
-    # per-class device time for the roofline; kept out of `value` because ~10^4 event records per step
-    # cost a few percent of host-side launch throughput.
-    ms_prof, prof = timed(False, args.steps, 0, True)
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        ms_dev, _ = timed(False, steps, warmup, False)
+        clocks = sampler.summary() if sampler else None
+        ms_io, prof, ms_prof = None, None, None
+        if profile_pass:
+            ms_io, _ = timed(True, steps, max(1, warmup // 3), False)
+            # same steps once more with a CUDA-event pair around every kernel class launch (engine stream): per-class
+            # device time for the roofline; kept out of `value`: ~10^4 event records per step cost host launch throughput
+            ms_prof, prof = timed(False, steps, 0, True)
+            step(False, sync_before_prefill=True)            # what the prefill call costs the host when the queue is empty
+            eng.sync()
+        for s in sids:
+            eng.close_session(s)
+        return dict(ms_dev=ms_dev, ms_io=ms_io, ms_prof=ms_prof, prof=prof, host=host, clocks=clocks)
+
+    eng = make_engine(args.precision, max(B, seam_bmax), max(B, seam_bmax))
+    r = scripted(eng, B, args.steps, args.warmup)
+    seam_best, seam_probes = None, []
+    if not args.no_seam:
+        seam_best, seam_probes = seam_search(eng, B, seam_bmax, world, rng, args.seam_ticks, 4)
+    la64 = None
+    if not args.no_extras and args.precision == "bf16" and rank == 0 and world == 1 and max(B, seam_bmax) >= 64:
+        try:
+            la64 = config_localagreement_64(local_rank, eng=eng)
+        except Exception as e:                                            # noqa: BLE001
+            la64 = dict(error=repr(e))
+    eng.close()
+
+    exact, others = None, None
+    if not args.no_extras and args.precision == "bf16":
+        Bx = min(B, 32)
+        engx = make_engine("bf16x3", Bx, Bx)
+        rx = scripted(engx, Bx, 2, 3, profile_pass=False)
+        engx.close()
+        msx = rx["ms_dev"] / 2
+        exact = dict(mode="bf16x3 (WLK_PREC_BF16X3: split operands, 3 tcgen05 MMAs per product; fp32 activations, softmax, K/V)",
+                     parity="|dlogits| 2.4e-4 vs the reference at large-v3, tokens and frames identical (tests/test_gpu_large_v3.py)",
+                     value=Bx * world * CHUNK_S / (msx / 1e3), unit=UNIT, streams_per_gpu=Bx, ms_per_step=msx)
+        if rank == 0 and world == 1:
+            others = {c: (la64 if c == "localagreement-large-v3-64" and la64 is not None else run_side_config(c, local_rank))
+                      for c in CONFIGS[1:]}
 
     if rank == 0:
         peaks = load_peaks()
         total_streams = B * world
+        ms_dev, ms_io, prof, host = r["ms_dev"], r["ms_io"], r["prof"], r["host"]
         value = total_streams * CHUNK_S * args.steps / (ms_dev / 1e3)
-        e2e_value = total_streams * CHUNK_S * args.steps / (ms_e2e / 1e3)
         g = prof["gemm_enc"]
-        traffic = None                                     # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
-        tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-        if os.path.exists(tpath) and B == 96 and args.model == "large-v3":
-            traffic = json.load(open(tpath))["mean_dram_bytes_per_launch"]
+        traffic, tnote = None, "no ncu capture for this configuration"
+        for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tpath) and B == 96 and args.model == "large-v3":
+                tj = json.load(open(tpath))
+                traffic = tj["mean_dram_bytes_per_launch"]
+                tnote = (f"dram__bytes_read+write per launch, mean of one encoder layer's GEMMs, ncu --set full at 96 streams "
+                         f"(profiles/{name}); algorithmic {tj.get('algorithmic_bytes_per_launch', 2.04e9) / 1e9:.2f} GB")
+                break
         ach = g["flops"] / (g["ms"] / 1e3) / 1e12 if g["ms"] else 0.0
         mult = dict(mel=2, align=3)
         launches = int(sum(v["launches"] * mult.get(k, 1) for k, v in prof.items()))
         classes = {k: dict(ms_per_step=v["ms"] / args.steps, launches_per_step=v["launches"] / args.steps,
                            tflops=(v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] and v["flops"] else None)
                    for k, v in prof.items() if v["launches"]}
+        scripted_io = dict(value=total_streams * CHUNK_S * args.steps / (ms_io / 1e3), ms_per_step=ms_io / args.steps,
+                           note="the scripted tick with per-chunk H2D append + window shift and per-token D2H, engine driven directly")
+        if seam_best is not None:
+            e2e = dict(value=float(seam_best["streams"] * world), unit=UNIT,
+                       h2d_bytes_per_step=seam_best["streams"] * world * CHUNK * 4,
+                       d2h_bytes_per_step=int(seam_best["streams"] * world * 16 * (seam_best["mean_decode_iterations"] + 1)),
+                       how="largest probed B per GPU with p95(chunk arrival -> infer() returned) < 0.5 s and no backlog growth; "
+                           "B StreamingAlignAtt policies on B threads over BatchingEngine, real-time paced, staggered phases",
+                       best=seam_best, probes=[dict(streams=p["streams"], ok=p["ok_all_ranks"], p95_latency_s=p["p95_latency_s"],
+                                                    start_lag_last_third_s=p["start_lag_last_third_s"]) for p in seam_probes],
+                       scripted_with_io=scripted_io)
+        else:
+            e2e = dict(value=scripted_io["value"] if not seam_probes else 0.0, unit=UNIT, h2d_bytes_per_step=B * world * CHUNK * 4,
+                       d2h_bytes_per_step=B * world * 16 * (STEPS_PER_CHUNK + 1),
+                       how=("scripted tick with host chunks (seam run skipped)" if not seam_probes else
+                            "no probed stream count met p95 < 0.5 s through the seam"),
+                       probes=[dict(streams=p["streams"], ok=p["ok_all_ranks"], p95_latency_s=p["p95_latency_s"],
+                                    start_lag_last_third_s=p["start_lag_last_third_s"], errors=p["errors"]) for p in seam_probes],
+                       scripted_with_io=scripted_io)
         line = dict(
-            metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup,
+            metric=metric, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-            dtype="bf16", data="synthetic (seeded random weights at true large-v3 dims, synthetic speech-like audio)",
+            dtype="bf16" if args.precision == "bf16" else "bf16x3",
+            data="synthetic (seeded random weights at true large-v3 dims, synthetic speech-like audio)",
             config=dict(workload=workload, model=args.model, streams_per_gpu=B, parallelism=f"sessions sharded x{world}",
                         chunk_s=CHUNK_S, l2="working set (3.4 GB weights + per-stream KV) exceeds the 126 MB L2",
-                        rtf_per_stream=(ms_dev / args.steps / 1e3) / CHUNK_S),
-            e2e=dict(value=e2e_value, unit=unit, h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=d2h * world,
-                     ms_per_step=ms_e2e / args.steps),
+                        rtf_per_stream=(ms_dev / args.steps / 1e3) / CHUNK_S,
+                        frac_of_encoder_gemm_stream_ceiling=value / world / (peaks["bf16_tflops"] / 5.18),
+                        parity="bf16 mode: tokens identical to the reference at 64/64 teacher-forced steps on two large-v3 streams, "
+                               "max |dlogits| 0.075 (tests/test_gpu_large_v3.py, profiles/r02_parity_large_v3_bf16.json)"),
+            e2e=e2e,
             gpu_launches=launches,
-            clocks=clocks,
+            clocks=r["clocks"],
             roofline=dict(bound="tensor", kernel="gemm_tc2_kernel (cta_group::2 pair GEMM; encoder GEMMs, class gemm_enc)", achieved=ach,
                           peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=ach / peaks["bf16_tflops"], traffic=traffic,
-                          traffic_note="dram__bytes_read+write per launch, mean of one encoder layer's 4 GEMMs, ncu --set full at 96 "
-                                       "streams (profiles/r01_gemm_traffic.json); algorithmic 2.04 GB",
-                          peak_source=peaks["source"],
+                          traffic_note=tnote, peak_source=peaks["source"],
                           flops_per_launch=g["flops"] / max(1, g["launches"]), ms_per_launch=g["ms"] / max(1, g["launches"])),
             kernel_classes=classes,
-            profiled_ms_per_step=ms_prof / args.steps,
-            host_enqueue_ms=dict(encode_call=1e3 * host["encode"] / host["n"], prefill_call=1e3 * host["prefill"] / host["n"],
-                                 decode_step_call=1e3 * host["step"] / host["n"] / STEPS_PER_CHUNK,
-                                 note="host time inside the (asynchronous) engine calls, averaged over all passes"),
+            profiled_ms_per_step=r["ms_prof"] / args.steps,
+            host_enqueue_ms=dict(encode_call=1e3 * host["encode"] / max(1, host["n"]), prefill_call=1e3 * host["prefill"] / max(1, host["n"]),
+                                 prefill_call_queue_empty=1e3 * host["prefill_synced"] / max(1, host["ns"]),
+                                 decode_step_call=1e3 * host["step"] / max(1, host["n"]) / STEPS_PER_CHUNK,
+                                 note="host time inside the asynchronous engine calls; prefill_call is back-pressure of the ~1000-deep "
+                                      "launch queue behind the encoder's launches -- with the queue drained first it is prefill_call_queue_empty"),
         )
+        if exact is not None:
+            line["exact_mode"] = exact
+        if others is not None:
+            line["other_configs"] = others
         if not args.no_cpu_baseline:
-            sd_cpu = sd if world == 1 or rank == 0 else None
-            sec, threads = cpu_stream_chunk_seconds(dims, sd_cpu, heads, 2)
-            line["cpu_baseline"] = dict(value=CHUNK_S / sec, unit=unit, cores=threads, kind="port",
-                                        sample="2 stream-chunk steps of the same workload (1 stream), oracle port of the "
-                                               "reference CPU path, all host threads", seconds_per_stream_chunk=sec)
+            line["cpu_baseline"] = cpu_baseline_leg(dims, sd, heads, 2)
         print(json.dumps(line))
-    for s in sids:
-        eng.close_session(s)
-    eng.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -138,19 +138,23 @@ def time_parallel_single_thread(model, dims, prefix_len, steps, procs, timeout_s
     """`procs` single-thread streams in parallel (figure ii): fork one process per stream (the
     model's weights are shared copy-on-write), each runs ONE stream-chunk; returns (wall seconds, finished).
     Must be called before this process has run any multi-threaded torch op (OpenMP pools do not survive fork)."""
+    import select
     import torch
     torch.set_num_threads(1)
-    r, w = os.pipe()
-    t0 = time.perf_counter()
+    r, w = os.pipe()              # children -> parent: b"r" ready, b"1" chunk done, b"0" failed
+    gr, gw = os.pipe()            # parent -> children: the start signal (one byte each)
     pids = []
     for i in range(procs):
         pid = os.fork()
         if pid == 0:
             ok = b"0"
             try:
-                os.close(r)
+                os.close(r); os.close(gw)
                 torch.set_num_threads(1)
-                RefStream(model, dims, prefix_len, steps, seed=10 + i).chunk()
+                st = RefStream(model, dims, prefix_len, steps, seed=10 + i)
+                os.write(w, b"r")
+                os.read(gr, 1)
+                st.chunk()
                 ok = b"1"
             finally:
                 try:
@@ -158,24 +162,32 @@ def time_parallel_single_thread(model, dims, prefix_len, steps, procs, timeout_s
                 finally:
                     os._exit(0)
         pids.append(pid)
-    os.close(w)
-    done = 0
-    import select
-    deadline = t0 + timeout_s
-    t_last = t0
-    while done < procs:
-        left = deadline - time.perf_counter()
-        if left <= 0:
-            break
-        rl, _, _ = select.select([r], [], [], left)
-        if not rl:
-            break
-        data = os.read(r, 4096)
-        if not data:
-            break
-        done += data.count(b"1")
-        t_last = time.perf_counter()
-    wall = (t_last if done == procs else time.perf_counter()) - t0
+    os.close(w); os.close(gr)
+
+    def collect(token, deadline):
+        n = 0
+        while n < procs:
+            left = deadline - time.perf_counter()
+            if left <= 0:
+                break
+            rl, _, _ = select.select([r], [], [], left)
+            if not rl:
+                break
+            data = os.read(r, 4096)
+            if not data:
+                break
+            n += data.count(token)
+            if token == b"r" and data.count(b"0"):
+                break
+        return n
+
+    ready = collect(b"r", time.perf_counter() + 120.0)
+    done, wall = 0, 0.0
+    if ready == procs:
+        t0 = time.perf_counter()
+        os.write(gw, b"g" * procs)
+        done = collect(b"1", t0 + timeout_s)
+        wall = time.perf_counter() - t0
     for pid in pids:
         if done < procs:
             try:
@@ -186,5 +198,5 @@ def time_parallel_single_thread(model, dims, prefix_len, steps, procs, timeout_s
             os.waitpid(pid, 0)
         except ChildProcessError:
             pass
-    os.close(r)
+    os.close(r); os.close(gw)
     return wall, done

@@ -350,10 +350,24 @@ class AlignAttHooks:
         self._n_audio = 0
         self._init_state(cfg)
 
+    def close(self) -> None:
+        """Release the session (and its beam forks) now: ~350 MB of device state at large-v3.  The online processor's
+        teardown should call this; ``__del__`` is only a backstop (the _BeamInference <-> hooks cycle leaves collection
+        to the cyclic GC, and under connection churn the engine would run out of sessions first)."""
+        if getattr(self, "_closed", False):
+            return
+        self._closed = True
+        for sid in reversed(getattr(self, "beam_sids", [self.sid])):         # forks before their parent
+            try:
+                self.engine.close_session(sid)
+            except Exception:
+                pass
+        if getattr(self.state, "inference", None) is not None:
+            self.state.inference.hooks = None                                # break the cycle
+
     def __del__(self):
         try:
-            for sid in reversed(getattr(self, "beam_sids", [self.sid])):     # forks before their parent
-                self.engine.close_session(sid)
+            self.close()
         except Exception:
             pass
 

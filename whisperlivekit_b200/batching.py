@@ -17,7 +17,8 @@ concurrent calls of the same kind into one C-ABI call:
 
 Semantics are unchanged: one call in flight per session (as the reference guarantees), results are what the
 single-session call would have returned (the batched kernels are batch-invariant: tests/test_gpu_parity.py
-``test_batched_equals_single``), errors are delivered to exactly the callers of the failing batch.
+``test_batched_equals_single``); when a merged call fails its requests are replayed one by one, so an error reaches
+only the caller whose session caused it.
 ``submit()`` returns a ``concurrent.futures.Future`` so an asyncio caller can ``await asyncio.wrap_future(f)``
 instead of parking an OS thread per stream.
 """
@@ -175,22 +176,32 @@ class BatchingEngine:
             if batch:
                 self._execute(batch)
 
-    def _execute(self, batch: List[_Request]) -> None:
+    def _call(self, batch: List[_Request]):
         op = batch[0].op
         sids = [s for r in batch for s in r.sids]
         payload, static = batch[0].payload
         per_session, shared = _OPS[op]
+        args = [sids]
+        if per_session:
+            args.append([item for r in batch for item in r.payload[0][0]])
+        if shared:
+            args.append(list(payload[0]))
+        with self._lock:
+            return sids, getattr(self.engine, op)(*args, **static)
+
+    def _execute(self, batch: List[_Request]) -> None:
+        op = batch[0].op
         try:
-            args = [sids]
-            if per_session:
-                args.append([item for r in batch for item in r.payload[0][0]])
-            if shared:
-                args.append(list(payload[0]))
-            with self._lock:
-                out = getattr(self.engine, op)(*args, **static)
-        except BaseException as e:                      # delivered to the callers of this batch only
+            sids, out = self._call(batch)
+        except BaseException as e:                      # noqa: BLE001
+            if len(batch) == 1:
+                batch[0].future.set_exception(e)
+                return
+            # One stream's error (n_text_ctx overflow, closed session, decode before encode ...) must not abort the
+            # other callers of the merged call: the engine validates a batch before it touches any session, so the
+            # requests are replayed one by one and only the offending caller sees its exception.
             for r in batch:
-                r.future.set_exception(e)
+                self._execute([r])
             return
         st = self.stats
         st["calls"] += 1
