@@ -61,23 +61,50 @@ def make_b200_alignatt_class():
 
 
 def install(precision: str = "bf16", device: int = 0, max_sessions: int = 64, max_batch: int = 64,
-            batching: bool = True, max_wait_s: float = 0.002):
+            batching: bool = True, max_wait_s: float = 0.002, engine_factory=None):
     """Route WhisperLiveKit's SimulStreaming backend through the B200 engine (call once, before
     TranscriptionEngine is constructed).  With ``batching`` the per-session calls of the worker threads
-    (audio_processor.py:543-551) are coalesced into batched C-ABI calls by batching.BatchingEngine."""
+    (audio_processor.py:543-551) are coalesced into batched C-ABI calls by batching.BatchingEngine.
+
+    ``engine_factory(torch_whisper) -> engine`` replaces the construction of the CUDA engine; the CPU tests pass the
+    oracle engine through it so that the registration itself (the symbols swapped below) is exercised without a GPU.
+    Returns the B200AlignAtt class; ``uninstall()`` restores the reference's symbols."""
     import whisperlivekit.simul_whisper.backend as be
     cls = make_b200_alignatt_class()
-    be.AlignAtt = cls
-    orig_load = be.SimulStreamingASR.load_model
+    if not hasattr(be, "_b200_saved"):
+        be._b200_saved = (be.AlignAtt, be.SimulStreamingASR.load_model, be.SimulStreamingOnlineProcessor.__del__)
+    be.AlignAtt = cls                                   # what _create_alignatt instantiates (backend.py:61-71)
+    orig_load = be._b200_saved[1]
 
-    def load_model(self, *a, **k):
+    def load_model(self, *a, **k):                      # backend.py:530-553
         torch_model = orig_load(self, *a, **k)
-        eng = engine_from_torch_whisper(torch_model, precision=precision, device=device,
-                                        max_sessions=max_sessions, max_batch=max_batch)
+        if engine_factory is not None:
+            eng = engine_factory(torch_model)
+        else:
+            eng = engine_from_torch_whisper(torch_model, precision=precision, device=device,
+                                            max_sessions=max_sessions, max_batch=max_batch)
         if batching:
             from .batching import BatchingEngine
             eng = BatchingEngine(eng, max_batch=max_batch, max_wait_s=max_wait_s)
         return B200WhisperModel(eng)
 
+    orig_del = be._b200_saved[2]
+
+    def processor_del(self):                            # backend.py:284-290: the session's device state dies with it
+        try:
+            model = getattr(self, "model", None)
+            if model is not None and hasattr(model, "close"):
+                model.close()
+        finally:
+            orig_del(self)
+
     be.SimulStreamingASR.load_model = load_model
+    be.SimulStreamingOnlineProcessor.__del__ = processor_del
     return cls
+
+
+def uninstall():
+    import whisperlivekit.simul_whisper.backend as be
+    if hasattr(be, "_b200_saved"):
+        be.AlignAtt, be.SimulStreamingASR.load_model, be.SimulStreamingOnlineProcessor.__del__ = be._b200_saved
+        del be._b200_saved
