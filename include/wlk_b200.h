@@ -224,6 +224,19 @@ int wlk_qwen_append_audio(wlk_qwen* q, const int32_t* sids, int n, const float* 
 int wlk_qwen_flush_pending(wlk_qwen* q, const int32_t* sids, int n, float* out_host, int64_t out_capacity_rows,
                            int32_t* out_row_offsets);
 
+/* =====================================================================================
+ * Step after the diarization forward.  Replaces SortformerDiarizationOnline.
+ * _process_predictions (reference whisperlivekit/diarization/sortformer_backend.py:313-363): for every stream the last
+ * len_prediction[i] frames of its device-resident predictions preds_dev[i] = [n_frames_total[i]][n_spk] fp32 are reduced
+ * to argmax over the first max_speakers channels and run-length encoded; only the segments are copied to the host:
+ * seg_out_host[i][k] = (speaker, first frame, end frame) in frames of the chunk, k < seg_count_host[i] <= max_seg.
+ * Times are the caller's (round(base_time + frame * frame_duration, 2), :343-361).  n_spk < max_speakers is the
+ * reference's RuntimeError (:316-319).
+ * ===================================================================================== */
+int wlk_diar_segments(int device, const float* const* preds_dev, const int32_t* n_frames_total,
+                      const int32_t* len_prediction, int n_streams, int n_spk, int max_speakers,
+                      int32_t* seg_out_host, int32_t* seg_count_host, int max_seg);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,7 @@ SIGNATURES = {
     "wlk_qwen_forward_chunk": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int64, _vp]),
     "wlk_qwen_append_audio": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int64, _vp, C.c_int32]),
     "wlk_qwen_flush_pending": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int64, _vp]),
+    "wlk_diar_segments": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int]),
     "wlk_session_append_pcm16": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64]),
     "wlk_session_fork": (C.c_int, [_vp, C.c_int32, _vp]),
     "wlk_sessions_gather_decoder": (C.c_int, [_vp, _vp, _vp, C.c_int]),
