@@ -623,11 +623,17 @@ def main():
             eng.close_session(s)
         return dict(ms_dev=ms_dev, ms_io=ms_io, ms_prof=ms_prof, prof=prof, host=host, clocks=clocks)
 
+    def note(msg):
+        if rank == 0:
+            print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
     eng = make_engine(args.precision, max(B, seam_bmax), max(B, seam_bmax))
     r = scripted(eng, B, args.steps, args.warmup)
+    note(f"scripted tick: {r['ms_dev'] / args.steps:.1f} ms device-resident, {r['ms_io'] / args.steps:.1f} ms with host chunks")
     seam_best, seam_probes = None, []
     if not args.no_seam:
         seam_best, seam_probes = seam_search(eng, B, seam_bmax, world, rng, args.seam_ticks, 4)
+        note("seam probes: " + json.dumps(seam_probes))
     la64 = None
     if not args.no_extras and args.precision == "bf16" and rank == 0 and world == 1 and max(B, seam_bmax) >= 64:
         try:
@@ -643,6 +649,7 @@ def main():
         rx = scripted(engx, Bx, 2, 3, profile_pass=False)
         engx.close()
         msx = rx["ms_dev"] / 2
+        note(f"bf16x3 tick at {Bx} streams: {msx:.1f} ms")
         exact = dict(mode="bf16x3 (WLK_PREC_BF16X3: split operands, 3 tcgen05 MMAs per product; fp32 activations, softmax, K/V)",
                      parity="|dlogits| 2.4e-4 vs the reference at large-v3, tokens and frames identical (tests/test_gpu_large_v3.py)",
                      value=Bx * world * CHUNK_S / (msx / 1e3), unit=UNIT, streams_per_gpu=Bx, ms_per_step=msx)
@@ -721,7 +728,10 @@ def main():
         if others is not None:
             line["other_configs"] = others
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_leg(dims, sd, heads, 2)
+            try:
+                line["cpu_baseline"] = cpu_baseline_leg(dims, sd, heads, 2)
+            except Exception as e:                                            # noqa: BLE001  (the line must still print)
+                line["cpu_baseline"] = dict(value=None, error=repr(e))
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

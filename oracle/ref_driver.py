@@ -74,7 +74,8 @@ class RefStream:
                              frame_threshold=25)
         self.torch = torch
         self.a = AlignAtt(cfg=cfg, loaded_model=model)
-        self.steps = steps
+        self.a.device = "cpu"             # AlignAtt picks 'cuda' whenever a GPU is visible (simul_whisper.py:134); this arm
+        self.steps = steps                # times the reference's CPU backend: the model and every tensor stay on the host
         audio = synthetic_audio(30.0, seed=seed)
         for c in range(0, len(audio), CHUNK):                       # 60 segments of 0.5 s: the window is full
             self.a.insert_audio(torch.from_numpy(audio[c:c + CHUNK]))
