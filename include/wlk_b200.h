@@ -237,6 +237,26 @@ int wlk_diar_segments(int device, const float* const* preds_dev, const int32_t* 
                       const int32_t* len_prediction, int n_streams, int n_spk, int max_speakers,
                       int32_t* seg_out_host, int32_t* seg_count_host, int max_seg);
 
+/* =====================================================================================
+ * Ingest step before the path: Silero VAD forward, batched over streams.  Replaces the
+ * per-stream, per-window call of the scripted model that VADIterator / FixedVADIterator make (reference
+ * whisperlivekit/silero_vad_iterator.py:20-29 init_jit_model, :288-331 FixedVADIterator.__call__ -> model(x[512], 16000)).
+ * Tensor names are the scripted model's state_dict keys ("_model.stft.forward_basis_buffer", "_model.encoder.N.
+ * reparam_conv.weight|bias", "_model.decoder.rnn.weight_ih|weight_hh|bias_ih|bias_hh", "_model.decoder.decoder.2.weight|
+ * bias"; the "_model." prefix is optional).  A session holds what the model keeps between windows: the 64-sample context
+ * and the LSTM (h, c).  wlk_vad_forward: session i consumes windows [window_offsets[i], window_offsets[i+1]) of pcm_host
+ * ([windows][512] fp32, 16 kHz) in order and gets one speech probability per window in probs_host at the same index.
+ * ===================================================================================== */
+typedef struct wlk_vad wlk_vad;
+int wlk_vad_create(int device, int max_sessions, wlk_vad** out);
+int wlk_vad_destroy(wlk_vad* v);
+int wlk_vad_load_tensor(wlk_vad* v, const char* name, const float* host, int64_t n);
+int wlk_vad_session_open(wlk_vad* v, int32_t* sid);
+int wlk_vad_session_reset(wlk_vad* v, int32_t sid);       /* model.reset_states() */
+int wlk_vad_session_close(wlk_vad* v, int32_t sid);
+int wlk_vad_forward(wlk_vad* v, const int32_t* sids, int n, const float* pcm_host, const int32_t* window_offsets,
+                    float* probs_host);
+
 #ifdef __cplusplus
 }
 #endif
