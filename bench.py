@@ -105,7 +105,7 @@ def reference_available() -> bool:
 def cpu_baseline_leg(dims, sd, heads, n_chunks=2):
     """One stream, all host threads, `n_chunks` stream-chunks of the headline workload.  -> dict"""
     from oracle import ref_driver as rd
-    cores = rd.host_cores()
+    cores = rd.default_threads()
     if reference_available():
         model = rd.build_model(dims, sd, heads)
         per, threads = rd.time_single_stream(model, dims, PREFIX, STEPS_PER_CHUNK, n_chunks, cores, warmup=0)
@@ -117,7 +117,7 @@ def cpu_baseline_leg(dims, sd, heads, n_chunks=2):
         kind, what = "port", "oracle port of the reference CPU path (oracle/_ref not staged)"
     sec = float(np.mean(per))
     return dict(value=CHUNK_S / sec, unit=UNIT, cores=threads, kind=kind, cpu_model=rd.cpu_model(), nproc=os.cpu_count(),
-                sample=f"{n_chunks} stream-chunks of the same workload, 1 stream, {threads} threads; {what}",
+                cpu_quota=rd.cpu_quota(), sample=f"{n_chunks} stream-chunks of the same workload, 1 stream, {threads} threads; {what}",
                 seconds_per_stream_chunk=sec)
 
 
@@ -151,7 +151,7 @@ def reference_arm(args, dims, heads, metric, workload):
     from whisperlivekit_b200.weights import synthetic_state_dict
     import torch
     torch.set_num_threads(1)                                  # nothing multi-threaded before the fork of figure (ii)
-    cores = rd.host_cores()
+    cores = rd.default_threads()                              # torch's own default here, torchrun's OMP_NUM_THREADS=1 ignored
     sd = synthetic_state_dict(dims, seed=0)
     if not reference_available():
         per = oracle_port_chunks(dims, sd, heads, 1)
@@ -186,7 +186,8 @@ def reference_arm(args, dims, heads, metric, workload):
                             note="staged unmodified reference (oracle/_ref), `--backend whisper` path: its own AlignAtt hooks over "
                                  "its vendored torch Whisper, fp32, scripted to the same per-chunk work as the B200 arm"),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=fig_i.get("kind", "reference"),
-                                  cpu_model=rd.cpu_model(), nproc=os.cpu_count(), omp_env=os.environ.get("OMP_NUM_THREADS"),
+                                  cpu_model=rd.cpu_model(), nproc=os.cpu_count(), cpu_quota=rd.cpu_quota(),
+                                  omp_env=os.environ.get("OMP_NUM_THREADS"),
                                   sample=f"better of two figures ({best}); each step is one stream-chunk of the workload",
                                   one_stream_all_cores=fig_i, parallel_single_thread=fig_ii),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -223,17 +224,23 @@ def seam_probe(eng, B, n_ticks, warm_ticks, rng, phase_mode="staggered", context
     stats = dict(prefix=[], iters=[], stops={})
     slock = threading.Lock()
     errors = []
+    abort = threading.Event()                                                # the backlog ran away: the probe has failed
     t_start = time.perf_counter() + 0.3
 
     def worker(i):
         p, ph = pols[i], phases[i]
         try:
             for k in range(total):
+                if abort.is_set():
+                    lat[i, k:] = 10.0; lag[i, k:] = 10.0
+                    return
                 due = t_start + ph + k * CHUNK_S
                 now = time.perf_counter()
                 if now < due:
                     time.sleep(due - now)
                 t0 = time.perf_counter()
+                if k >= warm_ticks and t0 - due > 2.0:
+                    abort.set()
                 p.insert_audio(chunks[(i + k) % 8])                      # H2D of the chunk + window slide
                 tr = p.infer()
                 t1 = time.perf_counter()
@@ -261,14 +268,15 @@ def seam_probe(eng, B, n_ticks, warm_ticks, rng, phase_mode="staggered", context
     third = max(1, n_ticks // 3)
     lag_first, lag_last = float(G[:, :third].mean()), float(G[:, -third:].mean())
     p95 = float(np.percentile(L, 95))
-    ok = (not errors) and p95 < CHUNK_S and lag_last < 0.1 + lag_first and float(G[:, -1].max()) < CHUNK_S
-    return dict(streams=B, ok=bool(ok), phase=phase_mode, ticks=n_ticks, p50_latency_s=float(np.percentile(L, 50)),
+    ok = (not errors) and (not abort.is_set()) and p95 < CHUNK_S and lag_last < 0.1 + lag_first and float(G[:, -1].max()) < CHUNK_S
+    return dict(streams=B, ok=bool(ok), aborted=abort.is_set(), phase=phase_mode, ticks=n_ticks, p50_latency_s=float(np.percentile(L, 50)),
                 p95_latency_s=p95, max_latency_s=float(L.max()), start_lag_first_third_s=lag_first,
                 start_lag_last_third_s=lag_last, wall_s=wall, errors=errors[:3],
                 mean_prefix_tokens=float(np.mean(stats["prefix"])) if stats["prefix"] else 0.0,
                 mean_decode_iterations=float(np.mean(stats["iters"])) if stats["iters"] else 0.0, stops=stats["stops"],
                 engine_calls=bst["calls"], mean_sessions_per_call=bst["sessions"] / max(1, bst["calls"]),
-                max_sessions_in_call=bst["max_sessions_in_call"])
+                max_sessions_in_call=bst["max_sessions_in_call"], cohorts=bst["cohorts"],
+                mean_cohort=bst["cohort_sessions"] / max(1, bst["cohorts"]), max_cohort=bst["max_cohort"])
 
 
 def seam_search(eng, B0, Bmax, world, rng, n_ticks, warm_ticks):
@@ -375,8 +383,7 @@ def config_localagreement_64(device=0, streams=64, ticks=3, eng=None):
         eng.decode(sids, [prompt] * streams)
         toks = [list(prompt) for _ in sids]
         for _ in range(32):
-            eng.suppress(sids, sup)
-            r = eng.greedy_and_align(sids)
+            r = eng.select(sids, sup)
             for i, t in enumerate(r):
                 toks[i].append(t[0])
             eng.decode(sids, [[t[0]] for t in r])
@@ -562,8 +569,7 @@ def main():
                 host["encode"] += t1 - t0; host["prefill"] += t2 - t1; host["n"] += 1
             eng.no_speech_prob(sids)
             for _ in range(STEPS_PER_CHUNK):
-                eng.suppress(sids, sup)
-                r = eng.greedy_and_align(sids)
+                r = eng.select(sids, sup)                    # suppress -> greedy token/logprob -> alignment reduce -> frame
                 t3 = time.perf_counter()
                 eng.decode(sids, [[t[0]] for t in r])
                 if not sync_before_prefill:

@@ -138,6 +138,16 @@ int wlk_add_logit_bias(wlk_engine* e, int32_t sid, const int32_t* token_ids, con
 int wlk_greedy_and_align(wlk_engine* e, const int32_t* sids, int n, int32_t window_iters,
                          int32_t* token_out, float* logprob_out, int32_t* frame_out);
 
+/* One call for the "pick" half of a policy iteration (align_att_base.py:229-243): for every session first the
+ * first-iteration set first_ids (where first_mask[i] != 0: _suppress_blank_tokens), then suppress_ids
+ * (_apply_token_suppression), then logits[bias_tokens[k]] += bias_values[k] for k in [bias_offsets[i], bias_offsets[i+1])
+ * (_apply_dry_penalty), then exactly what wlk_greedy_and_align does.  Same results as the separate calls in that order;
+ * one lock acquisition, one staging upload and one device->host sync instead of four.  bias_* may be null.            */
+int wlk_select(wlk_engine* e, const int32_t* sids, int n, const int32_t* suppress_ids, int n_suppress,
+               const int32_t* first_ids, int n_first, const uint8_t* first_mask, const int32_t* bias_tokens,
+               const float* bias_values, const int32_t* bias_offsets, int32_t window_iters, int32_t* token_out,
+               float* logprob_out, int32_t* frame_out);
+
 /* ---- debug taps for parity tests (device -> host fp32) ---------------------------------*/
 int wlk_read_mel(wlk_engine* e, int32_t sid, float* out /* [n_mels,3000] */);
 int wlk_read_encoder(wlk_engine* e, int32_t sid, float* out /* [1500,d] */);

@@ -32,6 +32,34 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
+def default_threads() -> int:
+    """The intra-op thread count torch picks on this box when nothing overrides it (OMP_NUM_THREADS unset) -- what the
+    reference runs with by default; torchrun exports OMP_NUM_THREADS=1, which this ignores on purpose.  Bounded by the
+    cgroup CPU quota when there is one."""
+    import subprocess
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+    n = host_cores()
+    try:
+        out = subprocess.run([sys.executable, "-c", "import torch; print(torch.get_num_threads())"], env=env,
+                             capture_output=True, text=True, timeout=120).stdout.strip().splitlines()
+        n = int(out[-1])
+    except Exception:
+        pass
+    q = cpu_quota()
+    if q:
+        n = max(1, min(n, int(q)))
+    return n
+
+
+def cpu_quota():
+    """cgroup v2 cpu.max as a number of CPUs, or None when unlimited / unreadable."""
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        return None if quota == "max" else float(quota) / float(period)
+    except Exception:
+        return None
+
+
 def cpu_model() -> str:
     try:
         for line in open("/proc/cpuinfo"):
@@ -48,10 +76,21 @@ def build_model(dims, sd, heads):
     from oracle.stage_reference import import_staged_reference
     import_staged_reference()
     from whisperlivekit.whisper.model import ModelDimensions as RefDims, Whisper
-    m = Whisper(RefDims(*dims.as_tuple())).eval()
+    # The random initialisation of 1.5 G parameters (a minute of single-thread work at large-v3) would be overwritten by
+    # load_state_dict anyway: torch.nn.init's samplers are no-ops while the module is constructed.
+    import torch.nn.init as init
+    saved = {k: getattr(init, k) for k in ("kaiming_uniform_", "uniform_", "normal_", "trunc_normal_")}
+    try:
+        for k in saved:
+            setattr(init, k, lambda t, *a, **kw: t)
+        m = Whisper(RefDims(*dims.as_tuple())).eval()
+    finally:
+        for k, f in saved.items():
+            setattr(init, k, f)
     tsd = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
     missing, unexpected = m.load_state_dict(tsd, strict=False)
     assert not unexpected, unexpected
+    assert all("mask" in k or "alignment_heads" in k for k in missing), missing
     mask = torch.zeros(dims.n_text_layer, dims.n_text_head, dtype=torch.bool)
     for l, h in heads:
         mask[l, h] = True

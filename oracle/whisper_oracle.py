@@ -392,6 +392,18 @@ class OracleEngine:
         for tkn, b in zip(token_ids, biases):
             lg[tkn] = lg[tkn] + b
 
+    def select(self, sids, suppress, first_ids=(), first_mask=None, biases=None, window_iters: int = 16):
+        """The engine's fused "pick" call as the plain sequence of the reference's steps (align_att_base.py:229-243)."""
+        for i, sid in enumerate(sids):
+            if first_mask is not None and first_mask[i] and len(first_ids):
+                self.suppress([sid], first_ids)
+        self.suppress(sids, suppress)
+        if biases is not None:
+            for sid, b in zip(sids, biases):
+                if b:
+                    self.add_logit_bias(sid, [t for t, _ in b], [v for _, v in b])
+        return self.greedy_and_align(sids, window_iters)
+
     @torch.no_grad()
     def greedy_and_align(self, sids: Sequence[int], window_iters: int = 16):
         """-> list of (next_token, logprob, most_attended_frame) per session."""

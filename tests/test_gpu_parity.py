@@ -316,3 +316,39 @@ def test_beam_fork_and_gather_match_oracle():
     for s in reversed(sids):
         eng.close_session(s)
     eng.close()
+
+
+def test_fused_select_equals_elementary_calls():
+    """wlk_select (suppression sets + DRY biases + greedy + alignment reduction in one call) == the separate
+    wlk_suppress / wlk_add_logit_bias / wlk_greedy_and_align calls in the reference's order (align_att_base.py:229-243)."""
+    g, dims, sd, audio, heads = case_setup("micro")
+    eng = engine_for("micro", "fp32")
+    sup = eng.specials.alignatt_suppress_tokens()
+    blank = [eng.specials.blank, eng.specials.eot]
+    results = []
+    for fused in (False, True):
+        s0, s1 = eng.open_session(), eng.open_session()
+        eng.append_audio(s0, audio); eng.append_audio(s1, audio[:30000])
+        eng.encode([s0, s1])
+        eng.decode([s0, s1], [list(g["forced_prefix"]), list(g["forced_prefix"])[:3]])
+        out = []
+        for it in range(3):
+            first = [it == 0, False]
+            biases = [[(int(g["forced_steps"][0]), -2.0), (7, -0.5)] if it else [], [(11, -1.0)]]
+            if fused:
+                r = eng.select([s0, s1], sup, blank, first, biases, window_iters=16)
+            else:
+                if first[0]:
+                    eng.suppress([s0], blank)
+                eng.suppress([s0, s1], sup)
+                for s, b in zip((s0, s1), biases):
+                    if b:
+                        eng.add_logit_bias(s, [t for t, _ in b], [v for _, v in b])
+                r = eng.greedy_and_align([s0, s1], window_iters=16)
+            out.append((r, eng.read_logits(s0).copy(), eng.read_logits(s1).copy()))
+            eng.decode([s0, s1], [[r[0][0]], [r[1][0]]])
+        results.append(out)
+        eng.close_session(s0); eng.close_session(s1)
+    for a, b in zip(*results):
+        assert a[0] == b[0]
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])

@@ -73,6 +73,7 @@ SIGNATURES = {
     "wlk_qwen_forward_chunk": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int64, _vp]),
     "wlk_qwen_append_audio": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int64, _vp, C.c_int32]),
     "wlk_qwen_flush_pending": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int64, _vp]),
+    "wlk_select": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp]),
     "wlk_vad_create": (C.c_int, [C.c_int, C.c_int, _vp]),
     "wlk_vad_destroy": (C.c_int, [_vp]),
     "wlk_vad_load_tensor": (C.c_int, [_vp, C.c_char_p, _vp, C.c_int64]),

@@ -75,6 +75,24 @@ def dry_penalties(seq: Sequence[int], eot: int) -> List[Tuple[int, float]]:
     return [(tok, 1.0 * 2.0 ** (length - 2)) for tok, length in penalties.items() if length >= 2]
 
 
+def engine_select(eng, sids, suppress, first_ids, first_mask, biases, window_iters=16):
+    """The "pick" half of a policy iteration.  Engines with the fused entry point (WhisperEngine.select ->
+    wlk_select, BatchingEngine.select) take it in one call; a duck-typed engine that only has the elementary calls
+    gets the same steps in the same order."""
+    sel = getattr(eng, "select", None)
+    if sel is not None:
+        return sel(sids, suppress, first_ids, first_mask, biases, window_iters=window_iters)
+    for i, sid in enumerate(sids):
+        if first_mask[i] and len(first_ids):
+            eng.suppress([sid], list(first_ids))
+    if len(suppress):
+        eng.suppress(list(sids), list(suppress))
+    for sid, b in zip(sids, biases):
+        if b:
+            eng.add_logit_bias(sid, [t for t, _ in b], [v for _, v in b])
+    return eng.greedy_and_align(list(sids), window_iters=window_iters)
+
+
 @dataclass
 class InferTrace:
     """What one ``infer`` did -- compared token-for-token with the reference in tests."""
@@ -226,14 +244,13 @@ class StreamingAlignAtt:
                     tr.no_speech = True
                     tr.stop = "no_speech"
                     break
-                eng.suppress([sid], [self.sp.blank, self.sp.eot])            # _suppress_blank_tokens
+            first = new_segment                                              # _suppress_blank_tokens applies
             new_segment = False
-            eng.suppress([sid], self.suppress_tokens)                        # _apply_token_suppression
-            if cfg.dry_penalty:
-                pen = dry_penalties(current_tokens, self.sp.eot)             # _apply_dry_penalty
-                if pen:
-                    eng.add_logit_bias(sid, [t for t, _ in pen], [-a for _, a in pen])
-            tok, logprob, frame = eng.greedy_and_align([sid], window_iters=16)[0]
+            pen = dry_penalties(current_tokens, self.sp.eot) if cfg.dry_penalty else []     # _apply_dry_penalty
+            # _suppress_blank_tokens, _apply_token_suppression, _apply_dry_penalty, _update_tokens,
+            # _process_cross_attention and _get_attended_frames: one engine call (wlk_select)
+            tok, logprob, frame = engine_select(eng, [sid], self.suppress_tokens, [self.sp.blank, self.sp.eot], [first],
+                                                [[(t, -a) for t, a in pen]], window_iters=16)[0]
             if current_tokens[-1] == self.sp.eot:                            # decoding.py:282
                 tok = self.sp.eot
             current_tokens = current_tokens + [tok]
@@ -525,28 +542,37 @@ class AlignAttHooks:
             return self.engine.no_speech_prob([self.sid])[0] > self.cfg.nonspeech_prob
         return False
 
+    # The three logit edits below are recorded and applied, in this order, inside the one engine call that
+    # _update_tokens makes (wlk_select): the base class only passes `logits` through between them
+    # (align_att_base.py:229-237), so nothing can observe the difference, and a policy iteration costs two round
+    # trips to the engine (decode, select) instead of five.
     def _suppress_blank_tokens(self, logits):
-        self.engine.suppress(self.beam_sids, self._blank)
+        self._pend_first = True
         return logits
 
     def _apply_token_suppression(self, logits):
-        self.engine.suppress(self.beam_sids, self._suppress)
+        self._pend_suppress = True
         return logits
 
     def _apply_dry_penalty(self, logits, current_tokens):
         # the reference scans beam row 0 and penalises that token set on every row (align_att_base.py:501,535)
-        pen = dry_penalties(current_tokens[0].tolist(), self.tokenizer.eot)
-        if pen:
-            for sid in self.beam_sids:
-                self.engine.add_logit_bias(sid, [t for t, _ in pen], [-a for _, a in pen])
+        self._pend_bias = [(t, -a) for t, a in dry_penalties(current_tokens[0].tolist(), self.tokenizer.eot)]
         return logits
+
+    def _select(self):
+        n = len(self.beam_sids)
+        first, self._pend_first = getattr(self, "_pend_first", False), False
+        sup, self._pend_suppress = getattr(self, "_pend_suppress", False), False
+        bias, self._pend_bias = getattr(self, "_pend_bias", []), []
+        return engine_select(self.engine, self.beam_sids, self._suppress if sup else [], self._blank, [first] * n,
+                             [list(bias) for _ in range(n)], window_iters=16)
 
     def _update_tokens_beam(self, current_tokens, sum_logprobs):
         """whisper/decoding.py:317-376 (BeamSearchDecoder.update, unchanged, on the host) over the beams' fp32
         logits; its rearrange_kv_cache lands in wlk_sessions_gather_decoder.  The attended frames come from each
         row's own alignment history, which the reference does not re-index either."""
         import torch
-        res = self.engine.greedy_and_align(self.beam_sids, window_iters=16)
+        res = self._select()
         self._frames = [int(r[2]) for r in res]
         lg = torch.from_numpy(np.stack([self.engine.read_logits(sid) for sid in self.beam_sids]))
         return self.state.token_decoder.update(current_tokens, lg, sum_logprobs)
@@ -555,7 +581,7 @@ class AlignAttHooks:
         import torch
         if self.beam > 1:
             return self._update_tokens_beam(current_tokens, sum_logprobs)
-        tok, lp, frame = self.engine.greedy_and_align([self.sid], window_iters=16)[0]
+        tok, lp, frame = self._select()[0]
         eot = self.tokenizer.eot
         if int(current_tokens[0, -1]) == eot:                       # decoding.py:280-282
             tok = eot

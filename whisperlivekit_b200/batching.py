@@ -12,8 +12,17 @@ concurrent calls of the same kind into one C-ABI call:
     caller threads                      dispatcher thread
     --------------                      -----------------
     eng.encode([sid])   --submit-->     gather requests with the same (op, static args)
-    (blocks on a Future)                until every in-flight caller has submitted, or `max_wait_s` passed
+    (blocks on a Future)                until every caller of the running cohort has submitted, or `max_wait_s` passed
                          <--result--    engine.encode([sid_a, sid_b, ...]) ; split the results
+
+Cohorts.  A policy iteration (``infer()``: encode, prefill, then a data-dependent number of token steps, each a
+host sync) is bracketed by ``begin_iter()`` / ``end_iter()``.  Callers are admitted in COHORTS: while one cohort is
+inside its iteration, newly arriving callers wait at ``begin_iter()``; when the last member leaves, everybody waiting
+is admitted at once.  The members of a cohort advance in lockstep, so every engine call serves the whole cohort --
+without admission control, streams arriving at their own phases interleave their encodes with other streams' token
+steps and every call degenerates to a dozen sessions while costing the same fixed step latency.  The cohort size
+regulates itself: the longer a cohort takes, the more callers arrive meanwhile (n = arrival_rate x T(n)); an idle
+engine admits a lone caller immediately.
 
 Semantics are unchanged: one call in flight per session (as the reference guarantees), results are what the
 single-session call would have returned (the batched kernels are batch-invariant: tests/test_gpu_parity.py
@@ -34,7 +43,7 @@ from typing import Any, Dict, List, Sequence
 _OPS = {
     # WhisperEngine (AlignAtt hooks)
     "encode": (False, False), "decode": (True, False), "no_speech_prob": (False, False), "suppress": (False, True),
-    "greedy_and_align": (False, False),
+    "greedy_and_align": (False, False), "select": (True, True),
     # QwenTowerEngine (QwenAudioCausalKVEncoder.forward_chunk / StreamingMelExtractor.append per stream: mel_append)
     "forward_chunk": (True, False), "mel_append": (True, False), "mel_flush": (False, False),
     "flush_pending": (False, False),
@@ -65,9 +74,11 @@ class BatchingEngine:
         self._lock = threading.RLock()              # serialises every call into the wrapped engine
         self._cv = threading.Condition()
         self._pending: List[_Request] = []
-        self._inflight = 0                          # callers inside begin_iter()/end_iter()
+        self._cohort = set()                        # thread ids admitted to the running policy iteration
+        self._waiting = set()                       # thread ids parked in begin_iter() until the cohort drains
         self._stop = False
         self.stats: Dict[str, Any] = dict(calls=0, requests=0, sessions=0, max_sessions_in_call=0,
+                                          cohorts=0, cohort_sessions=0, max_cohort=0,
                                           by_op={op: dict(calls=0, sessions=0) for op in _BATCHED})
         self._thread = threading.Thread(target=self._run, name="wlk-b200-batcher", daemon=True)
         self._thread.start()
@@ -84,13 +95,36 @@ class BatchingEngine:
         return attr
 
     # -- bracket a caller's policy iteration: lets the dispatcher fire as soon as everybody has arrived --
+    def _admit(self) -> None:
+        """Condition held, cohort empty: everybody waiting becomes the next cohort."""
+        if self._waiting:
+            self._cohort, self._waiting = self._waiting, set()
+            st = self.stats
+            st["cohorts"] += 1
+            st["cohort_sessions"] += len(self._cohort)
+            st["max_cohort"] = max(st["max_cohort"], len(self._cohort))
+            self._cv.notify_all()
+
     def begin_iter(self) -> None:
+        me = threading.get_ident()
         with self._cv:
-            self._inflight += 1
+            self._waiting.add(me)
+            while not self._stop:
+                if not self._cohort:
+                    self._admit()
+                if me in self._cohort:
+                    return
+                self._cv.wait()
+            self._waiting.discard(me)
+            raise RuntimeError("BatchingEngine is closed")
 
     def end_iter(self) -> None:
+        me = threading.get_ident()
         with self._cv:
-            self._inflight = max(0, self._inflight - 1)
+            self._cohort.discard(me)
+            self._waiting.discard(me)
+            if not self._cohort:
+                self._admit()
             self._cv.notify_all()
 
     # -- submission ---------------------------------------------------------------------------------------
@@ -101,6 +135,8 @@ class BatchingEngine:
         key = (op,) + tuple(sorted((k, _freeze(v)) for k, v in static.items()))
         if op == "suppress":
             key += (_freeze(payload[0]),)
+        elif op == "select":
+            key += (_freeze(payload[1]),)
         req = _Request(op, key, sids, (payload, static))
         with self._cv:
             if self._stop:
@@ -123,6 +159,15 @@ class BatchingEngine:
 
     def greedy_and_align(self, sids, window_iters: int = 16):
         return self.submit("greedy_and_align", sids, window_iters=int(window_iters)).result()
+
+    def select(self, sids, suppress, first_ids=(), first_mask=None, biases=None, window_iters: int = 16):
+        """The fused pick (WhisperEngine.select); per session: (first-iteration flag, DRY bias pairs)."""
+        n = len(sids)
+        fm = list(first_mask) if first_mask is not None else [False] * n
+        bs = [list(b) for b in biases] if biases is not None else [[] for _ in range(n)]
+        items = [(bool(fm[i]), bs[i]) for i in range(n)]
+        shared = (tuple(int(t) for t in suppress), tuple(int(t) for t in first_ids))
+        return self.submit("select", sids, items, shared, window_iters=int(window_iters)).result()
 
     # Qwen3 tower engine
     def forward_chunk(self, sids, mels):
@@ -147,7 +192,7 @@ class BatchingEngine:
             same = [r for r in self._pending if r.key == first.key]
             n_sess = sum(len(r.sids) for r in same)
             waiting = len(self._pending)
-            everyone_here = self._inflight > 0 and waiting >= self._inflight
+            everyone_here = len(self._cohort) > 0 and waiting >= len(self._cohort)
             if n_sess >= self.max_batch or everyone_here:
                 break
             left = deadline - time.perf_counter()
@@ -181,6 +226,13 @@ class BatchingEngine:
         sids = [s for r in batch for s in r.sids]
         payload, static = batch[0].payload
         per_session, shared = _OPS[op]
+        if op == "select":
+            items = [item for r in batch for item in r.payload[0][0]]
+            suppress, first_ids = payload[1]
+            from .alignatt import engine_select          # one fused call, or the elementary ones on a duck-typed engine
+            with self._lock:
+                return sids, engine_select(self.engine, sids, list(suppress), list(first_ids), [m for m, _ in items],
+                                           [b for _, b in items], **static)
         args = [sids]
         if per_session:
             args.append([item for r in batch for item in r.payload[0][0]])

@@ -31,10 +31,20 @@ namespace {
 constexpr int BQ = 128, BKV = 128, DH = 64;
 constexpr int ATT_THREADS = 320;          // TMA warp, MMA warp, 8 softmax warps
 constexpr uint32_t TILE_BYTES = BQ * DH * 2;          // 16 KB: Q, K and V tiles all are 128 x 64 bf16
-constexpr uint32_t SM_Q = 0, SM_K = TILE_BYTES, SM_V = 3 * TILE_BYTES, SM_BAR = 5 * TILE_BYTES;
-constexpr uint32_t SM_XCH = SM_BAR + 128;             // row-half exchange: [2][2][128] floats
-constexpr uint32_t ATT_SMEM = SM_XCH + 2 * 2 * BQ * 4 + 1024;
-constexpr uint32_t TM_S = 0, TM_O = 128, TM_P = 192, TM_COLS = 256;
+// Shared-memory / TMEM layout.  X3 (WLK_PREC_BF16X3): every operand is two bf16 planes (hi, lo); Q K^T and P V are each
+// three MMAs (hi hi + lo hi + hi lo) into the same fp32 accumulator, P is split like the other operands, the output is
+// fp32.  Twice the tiles and 320 TMEM columns: one CTA per SM instead of two.
+template <bool X3> struct AttLayout {
+    static constexpr uint32_t NP = X3 ? 2 : 1;                               // planes per operand
+    static constexpr uint32_t SM_Q = 0;                                      // [NP] tiles
+    static constexpr uint32_t SM_K = NP * TILE_BYTES;                        // [2 stages][NP]
+    static constexpr uint32_t SM_V = SM_K + 2 * NP * TILE_BYTES;             // [2 stages][NP]
+    static constexpr uint32_t SM_BAR = SM_V + 2 * NP * TILE_BYTES;
+    static constexpr uint32_t SM_XCH = SM_BAR + 128;                         // row-half exchange: [2][2][128] floats
+    static constexpr uint32_t SMEM = SM_XCH + 2 * 2 * BQ * 4 + 1024;
+    static constexpr uint32_t TM_COLS = X3 ? 512 : 256;
+};
+constexpr uint32_t TM_S = 0, TM_O = 128, TM_P = 192, TM_PLO = 256;
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ float fast_exp2(float x) {      // MUFU.EX2, flush-to-zero, exp2(-inf) = 0
@@ -83,11 +93,16 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 //                per-session tensor map kept in global memory (`kv_maps[job.slot]`).  Alignment heads are
 //                skipped here: their rows need the exactly normalised probabilities exported, which the
 //                SIMT kernel produces.
-template <bool CROSS>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const CUtensorMap* __restrict__ kv_maps,
+template <bool CROSS, bool X3>
+__global__ void __launch_bounds__(ATT_THREADS, X3 ? 1 : 2)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_lo,
+               const CUtensorMap* __restrict__ kv_maps,
                const DecJob* __restrict__ jobs, int layer, const int32_t* __restrict__ align_rank,
-               int n_head, int d_model, bf16* __restrict__ out) {
+               int n_head, int d_model, void* __restrict__ out_ptr) {
+    static_assert(!(CROSS && X3), "the split-operand variant serves the encoder only");
+    using AL = AttLayout<X3>;
+    constexpr uint32_t SM_Q = AL::SM_Q, SM_K = AL::SM_K, SM_V = AL::SM_V, SM_BAR = AL::SM_BAR, SM_XCH = AL::SM_XCH;
+    constexpr uint32_t TM_COLS = AL::TM_COLS, NP = AL::NP;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - ptx::smem_u32(smem_raw));
@@ -128,6 +143,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const CUtensorMap* __rest
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tm);
+        if (X3) ptx::prefetch_tensormap(&tm_lo);
         if (CROSS) ptx::prefetch_tensormap(tm_kv);
         ptx::mbar_init(bar_q, 1);
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_kv_full + 8 * i, 1); ptx::mbar_init(bar_kv_empty + 8 * i, 1); }
@@ -145,14 +161,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const CUtensorMap* __rest
 
     if (warp == 0) {
         if (lane == 0) {
-            ptx::mbar_arrive_expect_tx(bar_q, TILE_BYTES);
+            ptx::mbar_arrive_expect_tx(bar_q, NP * TILE_BYTES);
             ptx::tma_load_2d(sbase + SM_Q, &tm, bar_q, q_col, q_row);
+            if (X3) ptx::tma_load_2d(sbase + SM_Q + TILE_BYTES, &tm_lo, bar_q, q_col, q_row);
             for (int j = 0; j < NT; ++j) {
                 const uint32_t s = j & 1, ph = (j >> 1) & 1;
                 ptx::mbar_wait(bar_kv_empty + 8 * s, ph ^ 1);
-                ptx::mbar_arrive_expect_tx(bar_kv_full + 8 * s, 2 * TILE_BYTES);
-                ptx::tma_load_2d(sbase + SM_K + s * TILE_BYTES, tm_kv, bar_kv_full + 8 * s, k_col, k_row + j * BKV);
-                ptx::tma_load_2d(sbase + SM_V + s * TILE_BYTES, tm_kv, bar_kv_full + 8 * s, v_col, v_row + j * BKV);
+                ptx::mbar_arrive_expect_tx(bar_kv_full + 8 * s, 2 * NP * TILE_BYTES);
+                ptx::tma_load_2d(sbase + SM_K + s * NP * TILE_BYTES, tm_kv, bar_kv_full + 8 * s, k_col, k_row + j * BKV);
+                ptx::tma_load_2d(sbase + SM_V + s * NP * TILE_BYTES, tm_kv, bar_kv_full + 8 * s, v_col, v_row + j * BKV);
+                if (X3) {
+                    ptx::tma_load_2d(sbase + SM_K + (s * NP + 1) * TILE_BYTES, &tm_lo, bar_kv_full + 8 * s, k_col, k_row + j * BKV);
+                    ptx::tma_load_2d(sbase + SM_V + (s * NP + 1) * TILE_BYTES, &tm_lo, bar_kv_full + 8 * s, v_col, v_row + j * BKV);
+                }
             }
         }
     } else if (warp == 1) {
@@ -166,20 +187,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const CUtensorMap* __rest
             ptx::tc_fence_after();
             if (lane == 0) {
                 const uint64_t dq = ptx::umma_desc_kmajor_sw128(sbase + SM_Q);
-                const uint64_t dk = ptx::umma_desc_kmajor_sw128(sbase + SM_K + s * TILE_BYTES);
+                const uint64_t dk = ptx::umma_desc_kmajor_sw128(sbase + SM_K + s * NP * TILE_BYTES);
+                const uint64_t dql = ptx::umma_desc_kmajor_sw128(sbase + SM_Q + TILE_BYTES);
+                const uint64_t dkl = ptx::umma_desc_kmajor_sw128(sbase + SM_K + (s * NP + 1) * TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < DH / 16; ++k)
+                for (int k = 0; k < DH / 16; ++k) {
                     ptx::umma_bf16_ss(tmem + TM_S, dq + 2 * k, dk + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                    if (X3) {
+                        ptx::umma_bf16_ss(tmem + TM_S, dql + 2 * k, dk + 2 * k, idesc_s, 1u);
+                        ptx::umma_bf16_ss(tmem + TM_S, dq + 2 * k, dkl + 2 * k, idesc_s, 1u);
+                    }
+                }
                 ptx::umma_commit(bar_s_full);
             }
             __syncwarp();
             ptx::mbar_wait(bar_p_full, j & 1);                // P of tile j is in TMEM, O_{j-1} was consumed
             ptx::tc_fence_after();
             if (lane == 0) {
-                const uint64_t dv = ptx::umma_desc_mnmajor_sw128(sbase + SM_V + s * TILE_BYTES, BKV * 128);
+                const uint64_t dv = ptx::umma_desc_mnmajor_sw128(sbase + SM_V + s * NP * TILE_BYTES, BKV * 128);
+                const uint64_t dvl = ptx::umma_desc_mnmajor_sw128(sbase + SM_V + (s * NP + 1) * TILE_BYTES, BKV * 128);
 #pragma unroll
-                for (int k = 0; k < BKV / 16; ++k)             // 16 keys = 16 V rows of 128 B = 2048 B = +128 encoded
+                for (int k = 0; k < BKV / 16; ++k) {           // 16 keys = 16 V rows of 128 B = 2048 B = +128 encoded
                     umma_bf16_ts(tmem + TM_O, tmem + TM_P + 8 * k, dv + 128 * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                    if (X3) {
+                        umma_bf16_ts(tmem + TM_O, tmem + TM_PLO + 8 * k, dv + 128 * k, idesc_o, 1u);
+                        umma_bf16_ts(tmem + TM_O, tmem + TM_P + 8 * k, dvl + 128 * k, idesc_o, 1u);
+                    }
+                }
                 ptx::umma_commit(bar_o_full);
                 ptx::umma_commit(bar_kv_empty + 8 * s);
             }
@@ -195,6 +229,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const CUtensorMap* __rest
         const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
         const uint32_t s_addr = tmem + lane_addr + TM_S + half * (BKV / 2);
         const uint32_t p_addr = tmem + lane_addr + TM_P + half * (BKV / 4);
+        const uint32_t plo_addr = tmem + lane_addr + TM_PLO + half * (BKV / 4);
         const uint32_t o_addr = tmem + lane_addr + TM_O + half * (DH / 2);
         float* xch = reinterpret_cast<float*>(sgen + SM_XCH);  // [2 parities][2 halves][128 rows]
         uint32_t xn = 0;
@@ -244,6 +279,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const CUtensorMap* __rest
                 float rs = 0.f, mx = -INFINITY;
                 auto emit = [&](const uint32_t* v, int c) {   // 16 scores -> 8 packed words of P
                     uint32_t pk[8];
+                    uint32_t pl[X3 ? 8 : 1];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
@@ -258,8 +294,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const CUtensorMap* __rest
                         rs += p0 + p1;
                         __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
                         pk[i] = *reinterpret_cast<uint32_t*>(&hb);
+                        if (X3) {                             // P = hi + lo like every other operand of this mode
+                            __nv_bfloat162 lb = __floats2bfloat162_rn(p0 - __low2float(hb), p1 - __high2float(hb));
+                            pl[i] = *reinterpret_cast<uint32_t*>(&lb);
+                        }
                     }
                     tmem_st_32x8(p_addr + c * 8, pk);
+                    if (X3) tmem_st_32x8(plo_addr + c * 8, pl);
                 };
                 ptx::tmem_ld_32x16(s_addr, va);
                 ptx::tmem_ld_wait();
@@ -300,11 +341,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const CUtensorMap* __rest
         ptx::mbar_wait(bar_o_full, (NT - 1) & 1);
         ptx::tc_fence_after();
         const float inv = 1.0f / (l + exchange(l));
-        bf16* o = out + (int64_t)(out_row + r) * d_model + h * DH + half * (DH / 2);
         uint32_t v[32];
         ptx::tmem_ld_32x32(o_addr, v);                        // warp-collective: before the row predicate
         ptx::tmem_ld_wait();
-        if (r < n_q) {
+        if (X3) {
+            float* o = reinterpret_cast<float*>(out_ptr) + (int64_t)(out_row + r) * d_model + h * DH + half * (DH / 2);
+            if (r < n_q) {
+#pragma unroll
+                for (int e4 = 0; e4 < 8; ++e4)
+                    reinterpret_cast<float4*>(o)[e4] = make_float4(__uint_as_float(v[e4 * 4 + 0]) * inv, __uint_as_float(v[e4 * 4 + 1]) * inv,
+                                                                   __uint_as_float(v[e4 * 4 + 2]) * inv, __uint_as_float(v[e4 * 4 + 3]) * inv);
+            }
+        } else if (r < n_q) {
+            bf16* o = reinterpret_cast<bf16*>(out_ptr) + (int64_t)(out_row + r) * d_model + h * DH + half * (DH / 2);
 #pragma unroll
             for (int e8 = 0; e8 < 4; ++e8) {
                 uint4 u;
@@ -333,10 +382,26 @@ void enc_attention_tcgen05(const void* qkv, int batch, int n_head, int d_model, 
               "qkv tensor map: %s", err.c_str());
     static bool seen[64] = {};
     if (first_on_device(seen))
-        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AttLayout<false>::SMEM));
     dim3 grid((N_CTX + BQ - 1) / BQ, n_head, batch);
-    attn_tc_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tm, nullptr, nullptr, 0, nullptr, n_head, d_model,
-                                                              reinterpret_cast<bf16*>(out));
+    attn_tc_kernel<false, false><<<grid, ATT_THREADS, AttLayout<false>::SMEM, st>>>(tm, tm, nullptr, nullptr, 0, nullptr, n_head, d_model, out);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// WLK_PREC_BF16X3: qkv arrives as two bf16 planes [batch*1500, 3d] (hi, lo) -- the split of the fp32 QKV GEMM output --
+// and the result is fp32 [batch*1500, d].
+void enc_attention_tcgen05_x3(const void* qkv_hi, const void* qkv_lo, int batch, int n_head, int d_model, float* out, cudaStream_t st) {
+    CUtensorMap tm, tml;
+    std::string err;
+    WLK_CHECK(make_tmap_bf16_2d(&tm, qkv_hi, (uint64_t)batch * N_CTX, (uint64_t)3 * d_model, (uint64_t)3 * d_model, BQ, DH, &err),
+              "qkv tensor map: %s", err.c_str());
+    WLK_CHECK(make_tmap_bf16_2d(&tml, qkv_lo, (uint64_t)batch * N_CTX, (uint64_t)3 * d_model, (uint64_t)3 * d_model, BQ, DH, &err),
+              "qkv lo tensor map: %s", err.c_str());
+    static bool seen[64] = {};
+    if (first_on_device(seen))
+        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AttLayout<true>::SMEM));
+    dim3 grid((N_CTX + BQ - 1) / BQ, n_head, batch);
+    attn_tc_kernel<false, true><<<grid, ATT_THREADS, AttLayout<true>::SMEM, st>>>(tm, tml, nullptr, nullptr, 0, nullptr, n_head, d_model, out);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -357,11 +422,10 @@ void dec_cross_attention_tcgen05(const void* q, int total_rows, const DecJob* jo
               "query tensor map: %s", err.c_str());
     static bool seen[64] = {};
     if (first_on_device(seen))
-        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AttLayout<false>::SMEM));
     dim3 grid((max_rows + BQ - 1) / BQ, n_head, n_jobs);
-    CUDA_CHECK(launch_pdl(attn_tc_kernel<true>, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM, st, tm,
-                          reinterpret_cast<const CUtensorMap*>(kv_maps_dev), jobs, layer, align_rank, n_head, d_model,
-                          reinterpret_cast<bf16*>(out)));
+    CUDA_CHECK(launch_pdl(attn_tc_kernel<true, false>, grid, dim3(ATT_THREADS), (size_t)AttLayout<false>::SMEM, st, tm, tm,
+                          reinterpret_cast<const CUtensorMap*>(kv_maps_dev), jobs, layer, align_rank, n_head, d_model, out));
 }
 
 }  // namespace wlk

@@ -545,7 +545,13 @@ void run_encoder(wlk_engine* e, const int32_t* sids, int n, void** xkv_dev) {
             run_gemm(e, g, WLK_KC_GEMM_ENC); }
         {   ProfScope ps(e, WLK_KC_ATTN_ENC, 4.0 * n * D.n_audio_head * (double)N_CTX * N_CTX * 64,
                          (double)M * 4 * d * es);
-            if (e->attn_backend == WLK_BACKEND_TCGEN05)
+            if (e->attn_backend == WLK_BACKEND_TCGEN05 && e->wt == DT_BF16X2) {
+                // split the fp32 q|k|v into (hi, lo) planes (the GEMM operand scratch is idle between GEMMs)
+                bf16* hi = reinterpret_cast<bf16*>(e->a_split);
+                bf16* lo = hi + e->a_split_elems;
+                split_f32_planes_async(reinterpret_cast<const float*>(e->qkv), hi, lo, (int64_t)M * 3 * d, e->st);
+                enc_attention_tcgen05_x3(hi, lo, n, D.n_audio_head, d, reinterpret_cast<float*>(e->att), e->st);
+            } else if (e->attn_backend == WLK_BACKEND_TCGEN05)
                 enc_attention_tcgen05(e->qkv, n, D.n_audio_head, d, e->att, e->st, e->num_sms);
             else
                 enc_attention_simt(e->qkv, e->act, n, D.n_audio_head, d, e->att, e->st); }
@@ -873,8 +879,12 @@ void create_engine(const wlk_dims* dims, const wlk_config* cfg, wlk_engine** out
     e->attn_backend = cfg->attn_backend != WLK_BACKEND_AUTO ? cfg->attn_backend
                       : (e->act == DT_BF16 ? WLK_BACKEND_TCGEN05 : WLK_BACKEND_SIMT);
     if (e->act != DT_BF16) { e->gemm_backend = WLK_BACKEND_SIMT; e->attn_backend = WLK_BACKEND_SIMT; }
-    // BF16X3: fp32 activations and fp32 SIMT softmax / LayerNorm, every GEMM on the tensor cores with split operands
-    if (e->wt == DT_BF16X2) e->gemm_backend = WLK_BACKEND_TCGEN05;
+    // BF16X3: fp32 activations, LayerNorm and decoder attention; every GEMM and the encoder attention on the tensor
+    // cores with split operands (WLK_BACKEND_SIMT for the attention keeps the fp32 SIMT kernel: a test reference)
+    if (e->wt == DT_BF16X2) {
+        e->gemm_backend = WLK_BACKEND_TCGEN05;
+        e->attn_backend = cfg->attn_backend == WLK_BACKEND_SIMT ? WLK_BACKEND_SIMT : WLK_BACKEND_TCGEN05;
+    }
     CUDA_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     {   const char* v = getenv("WLK_GRAPHS"); e->graphs_on = !(v && v[0] == '0'); }
     for (auto& t : e->timers) CUDA_CHECK(cudaEventCreate(&t));
@@ -945,7 +955,7 @@ void create_engine(const wlk_dims* dims, const wlk_config* cfg, wlk_engine** out
         e->a_split_elems = (m + 7) / 8 * 8;
         e->a_split = dmalloc_bytes(e->a_split_elems * 2 * 2, acct);
     }
-    e->stg_bytes = (size_t)B * 1024 + R * 16 + 65536 + 1024 * 8;
+    e->stg_bytes = (size_t)B * 2048 + R * 16 + 65536 + 1024 * 8 * 4;
     CUDA_CHECK(cudaMallocHost(&e->stg_host, e->stg_bytes));
     e->stg_dev = reinterpret_cast<uint8_t*>(dmalloc_bytes(e->stg_bytes, acct));
     e->res_dev = dmalloc<StepResult>(e, B, acct);
@@ -1370,6 +1380,65 @@ int wlk_greedy_and_align(wlk_engine* e, const int32_t* sids, int n, int32_t wind
     }
     sg.upload();
     {   ProfScope ps(e, WLK_KC_LOGITS);
+        greedy_pick(lj_dev, n, e->dims.n_vocab, e->res_dev, e->st); }
+    {   ProfScope ps(e, WLK_KC_ALIGN);
+        align_reduce(lj_dev, n, e->n_align, e->dims.n_text_ctx, e->res_dev, e->st); }
+    CUDA_CHECK(cudaMemcpyAsync(e->res_host, e->res_dev, sizeof(StepResult) * n, cudaMemcpyDeviceToHost, e->st));
+    CUDA_CHECK(cudaStreamSynchronize(e->st));
+    for (int i = 0; i < n; ++i) {
+        token_out[i] = e->res_host[i].token; logprob_out[i] = e->res_host[i].logprob; frame_out[i] = e->res_host[i].frame;
+    }
+    WLK_API_END
+}
+
+// The whole "pick" half of a policy iteration in one call (one lock, one staging upload, one sync): suppression sets,
+// DRY biases, greedy token + logprob, alignment reduction and attended frame.
+int wlk_select(wlk_engine* e, const int32_t* sids, int n, const int32_t* suppress_ids, int n_suppress,
+               const int32_t* first_ids, int n_first, const uint8_t* first_mask, const int32_t* bias_tokens,
+               const float* bias_values, const int32_t* bias_offsets, int32_t window_iters, int32_t* token_out,
+               float* logprob_out, int32_t* frame_out) {
+    WLK_API_BEGIN
+    LOCK(e);
+    WLK_CHECK(sids && token_out && logprob_out && frame_out && n >= 1 && n <= e->cfg.max_batch && window_iters >= 1, "bad arguments");
+    WLK_CHECK(n_suppress >= 0 && n_suppress <= 4096 && n_first >= 0 && n_first <= 64, "bad suppression lists");
+    const int n_bias = bias_offsets ? bias_offsets[n] : 0;
+    WLK_CHECK(n_bias >= 0 && n_bias <= 64 * n, "bad bias lists");
+    Stager sg(e);
+    LogitJob* lj_dev; LogitJob* lj = sg.host<LogitJob>(n, &lj_dev);
+    LogitJob* fj_dev; LogitJob* fj = sg.host<LogitJob>(n, &fj_dev);
+    int32_t* sup_dev; int32_t* sup = sg.host<int32_t>(n_suppress > 0 ? n_suppress : 1, &sup_dev);
+    int32_t* fst_dev; int32_t* fst = sg.host<int32_t>(n_first > 0 ? n_first : 1, &fst_dev);
+    int32_t* bj_dev; int32_t* bj = sg.host<int32_t>(n_bias > 0 ? n_bias : 1, &bj_dev);
+    int32_t* bt_dev; int32_t* bt = sg.host<int32_t>(n_bias > 0 ? n_bias : 1, &bt_dev);
+    float* bv_dev; float* bv = sg.host<float>(n_bias > 0 ? n_bias : 1, &bv_dev);
+    int nf = 0;
+    for (int i = 0; i < n; ++i) {
+        Session& s = get_session(e, sids[i]);
+        WLK_CHECK(!s.iter_row_start.empty(), "session %d: no decode call in this epoch", sids[i]);
+        for (int j = 0; j < i; ++j) WLK_CHECK(sids[j] != sids[i], "session %d appears twice in the batch", sids[i]);
+        lj[i] = make_logit_job(e, s, window_iters, 0);
+        if (first_mask && first_mask[i]) fj[nf++] = lj[i];
+        if (n_bias) {
+            WLK_CHECK(bias_offsets[i + 1] >= bias_offsets[i], "bias offsets must be non-decreasing");
+            for (int k = bias_offsets[i]; k < bias_offsets[i + 1]; ++k) {
+                WLK_CHECK(bias_tokens[k] >= 0 && bias_tokens[k] < e->dims.n_vocab, "token %d out of range", bias_tokens[k]);
+                bj[k] = i; bt[k] = bias_tokens[k]; bv[k] = bias_values[k];
+            }
+        }
+    }
+    auto check_ids = [&](const int32_t* ids, int cnt, int32_t* dst) {
+        for (int i = 0; i < cnt; ++i) {
+            WLK_CHECK(ids[i] >= 0 && ids[i] < e->dims.n_vocab, "token %d out of range", ids[i]);
+            dst[i] = ids[i];
+        }
+    };
+    check_ids(suppress_ids, n_suppress, sup);
+    check_ids(first_ids, n_first, fst);
+    sg.upload();
+    {   ProfScope ps(e, WLK_KC_LOGITS);
+        if (nf && n_first) suppress_tokens(fj_dev, nf, fst_dev, n_first, e->st);
+        suppress_tokens(lj_dev, n, sup_dev, n_suppress, e->st);
+        add_logit_bias_jobs(lj_dev, bj_dev, bt_dev, bv_dev, n_bias, e->st);
         greedy_pick(lj_dev, n, e->dims.n_vocab, e->res_dev, e->st); }
     {   ProfScope ps(e, WLK_KC_ALIGN);
         align_reduce(lj_dev, n, e->n_align, e->dims.n_text_ctx, e->res_dev, e->st); }

@@ -355,6 +355,12 @@ void launch(const GemmArgs& g, const void* A_hi, const void* A_lo, cudaStream_t 
 
 }  // namespace
 
+void split_f32_planes_async(const float* src, bf16* hi, bf16* lo, int64_t n, cudaStream_t st) {
+    int grid = (int)std::min<int64_t>((n / 4 + 255) / 256, 148 * 8);
+    if (grid < 1) grid = 1;
+    CUDA_CHECK(launch_pdl(split_f32_kernel, dim3(grid), dim3(256), 0, st, src, hi, lo, n));
+}
+
 bool gemm_tcgen05_supported(const GemmArgs& g, std::string* why) {
     auto fail = [&](const char* m) { if (why) *why = m; return false; };
     const bool x3 = g.w_type == DT_BF16X2;
@@ -386,9 +392,7 @@ void gemm_tcgen05(const GemmArgs& g, cudaStream_t st, int num_sms, int variant) 
         const int64_t n = (int64_t)(g.M - 1) * g.lda + g.K;
         bf16* hi = reinterpret_cast<bf16*>(g.a_split);
         bf16* lo = hi + g.a_split_elems;
-        int grid = (int)std::min<int64_t>((n / 4 + 255) / 256, 148 * 8);
-        if (grid < 1) grid = 1;
-        CUDA_CHECK(launch_pdl(split_f32_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float*>(g.A), hi, lo, n));
+        split_f32_planes_async(reinterpret_cast<const float*>(g.A), hi, lo, n, st);
         A_hi = hi; A_lo = lo;
     }
     // Large problems go to the CTA-pair kernel (256x256 tiles, half the operand traffic per MAC); the

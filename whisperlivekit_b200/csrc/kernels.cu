@@ -857,6 +857,17 @@ __global__ void bias_kernel(float* lg, const int32_t* toks, const float* bias, i
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) lg[toks[i]] += bias[i];
 }
+__global__ void bias_jobs_kernel(const LogitJob* __restrict__ jobs, const int32_t* __restrict__ job_of, const int32_t* __restrict__ toks,
+                                 const float* __restrict__ bias, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) jobs[job_of[i]].logits_last[toks[i]] += bias[i];
+}
+void add_logit_bias_jobs(const LogitJob* jobs, const int32_t* job_of_dev, const int32_t* tokens_dev, const float* bias_dev, int n,
+                         cudaStream_t st) {
+    if (n <= 0) return;
+    bias_jobs_kernel<<<(n + 127) / 128, 128, 0, st>>>(jobs, job_of_dev, tokens_dev, bias_dev, n);
+    CUDA_CHECK(cudaGetLastError());
+}
 void add_logit_bias(float* logits, const int32_t* tokens_dev, const float* bias_dev, int n, cudaStream_t st) {
     if (n <= 0) return;
     bias_kernel<<<(n + 127) / 128, 128, 0, st>>>(logits, tokens_dev, bias_dev, n);

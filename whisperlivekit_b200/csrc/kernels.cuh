@@ -53,6 +53,9 @@ void embed_tokens(const int32_t* tokens_dev, const int32_t* pos_dev, const float
 // encoder self-attention over the fused qkv buffer [batch*1500, 3d] (q,k pre-scaled by d_head^-0.25)
 void enc_attention_simt(const void* qkv, int type, int batch, int n_head, int d_model, void* out, cudaStream_t st);
 void enc_attention_tcgen05(const void* qkv, int batch, int n_head, int d_model, void* out, cudaStream_t st, int num_sms);
+void enc_attention_tcgen05_x3(const void* qkv_hi, const void* qkv_lo, int batch, int n_head, int d_model, float* out, cudaStream_t st);
+// fp32 -> (hi, lo) bf16 planes on the stream (gemm_tc.cu)
+void split_f32_planes_async(const float* src, bf16* hi, bf16* lo, int64_t n, cudaStream_t st);
 
 struct DecJob {                 // one per session in a decode batch (device array)
     void* self_kv;              // [L][2][H][n_text_ctx][64]
@@ -95,6 +98,9 @@ struct StepResult { int32_t token; float logprob; int32_t frame; float no_speech
 void no_speech_prob(const LogitJob* jobs, int n, int n_vocab, int no_speech_token, StepResult* res, cudaStream_t st);
 void suppress_tokens(const LogitJob* jobs, int n, const int32_t* tokens_dev, int n_tokens, cudaStream_t st);
 void add_logit_bias(float* logits, const int32_t* tokens_dev, const float* bias_dev, int n, cudaStream_t st);
+// entry i adds bias[i] to logits_last[tokens[i]] of job job_of[i] (tokens are distinct within a job)
+void add_logit_bias_jobs(const LogitJob* jobs, const int32_t* job_of_dev, const int32_t* tokens_dev, const float* bias_dev, int n,
+                         cudaStream_t st);
 void greedy_pick(const LogitJob* jobs, int n, int n_vocab, StepResult* res, cudaStream_t st);
 void align_reduce(const LogitJob* jobs, int n, int n_align, int n_text_ctx, StepResult* res, cudaStream_t st);
 

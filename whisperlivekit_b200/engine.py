@@ -196,6 +196,27 @@ class WhisperEngine:
         L.check(self.lib.wlk_greedy_and_align(self.h, _ptr(s), len(s), int(window_iters), _ptr(tok), _ptr(lp), _ptr(fr)))
         return [(int(tok[i]), float(lp[i]), int(fr[i])) for i in range(len(s))]
 
+    def select(self, sids: Sequence[int], suppress: Sequence[int], first_ids: Sequence[int] = (),
+               first_mask: Optional[Sequence[bool]] = None, biases: Optional[Sequence[Sequence[Tuple[int, float]]]] = None,
+               window_iters: int = 16):
+        """suppress (+ first-iteration set where first_mask) -> DRY biases -> greedy token / logprob -> attended frame,
+        one C call (wlk_select).  biases[i] = [(token, value_to_add)] of session i."""
+        s, sup, fst = _i32(sids), _i32(suppress), _i32(first_ids)
+        n = len(s)
+        mask = np.ascontiguousarray(first_mask if first_mask is not None else np.zeros(n), np.uint8)
+        offs = np.zeros(n + 1, np.int32)
+        bt, bv = [], []
+        if biases is not None:
+            for i, b in enumerate(biases):
+                offs[i + 1] = offs[i] + len(b)
+                bt += [int(t) for t, _ in b]; bv += [float(v) for _, v in b]
+        btok, bval = _i32(bt), np.ascontiguousarray(bv, np.float32)
+        tok = np.zeros(n, np.int32); lp = np.zeros(n, np.float32); fr = np.zeros(n, np.int32)
+        L.check(self.lib.wlk_select(self.h, _ptr(s), n, _ptr(sup), len(sup), _ptr(fst), len(fst), _ptr(mask),
+                                    _ptr(btok) if len(bt) else None, _ptr(bval) if len(bt) else None,
+                                    _ptr(offs) if len(bt) else None, int(window_iters), _ptr(tok), _ptr(lp), _ptr(fr)))
+        return [(int(tok[i]), float(lp[i]), int(fr[i])) for i in range(n)]
+
     # -- debug taps -------------------------------------------------------------------
     def read_mel(self, sid: int) -> np.ndarray:
         out = np.zeros((self.dims.n_mels, 3000), np.float32)
