@@ -197,30 +197,103 @@ def reference_arm(args, dims, heads, metric, workload):
 # ------------------------------------------------------------------------------------------
 # through-the-seam, real-time paced load (e2e)
 # ------------------------------------------------------------------------------------------
-def seam_probe(eng, B, n_ticks, warm_ticks, rng, phase_mode="staggered", context_tokens=300):
-    """B StreamingAlignAtt policies on B threads over a BatchingEngine, one 0.5 s chunk per stream per 0.5 s of wall
-    clock.  Every policy starts mid-conversation: a full 30 s window, ~4 hypothesis tokens per second of window and
-    `context_tokens` of left context (a long stream saturates the reference's context at n_text_ctx - 20 tokens,
-    align_att_base.py:100-113).  -> dict(pass, p50/p95/max latency, lag, policy statistics)"""
+def _seam_policies(eng_like, eng, B, rng, context_tokens):
+    """B policies mid-conversation: a full 30 s window, ~4 hypothesis tokens per second of window and `context_tokens` of
+    left context (a long stream saturates the reference's context at n_text_ctx - 20 tokens, align_att_base.py:100-113)."""
     from whisperlivekit_b200.alignatt import AlignAttConfig, StreamingAlignAtt
-    from whisperlivekit_b200.batching import BatchingEngine
     from whisperlivekit_b200.weights import synthetic_audio
-    beng = BatchingEngine(eng, max_batch=eng.max_batch, max_wait_s=0.004)
     base = synthetic_audio(36.0, seed=7)
     pols = []
-    for i in range(B):
-        p = StreamingAlignAtt(beng, AlignAttConfig(nonspeech_prob=1.01))     # the no-speech exit would hide the decode loop on random weights
+    for _ in range(B):
+        p = StreamingAlignAtt(eng_like, AlignAttConfig(nonspeech_prob=1.01))     # the no-speech exit would hide the decode loop on random weights
         off = int(rng.integers(0, 16000 * 5))
-        win = base[off: off + WINDOW]
         p.segments = [CHUNK] * (WINDOW // CHUNK)
-        eng.append_audio(p.sid, win)
+        eng.append_audio(p.sid, base[off: off + WINDOW])
         p.tokens = [list(p.initial_tokens)] + [[int(t) for t in rng.integers(1000, 40000, 2)] for _ in range(WINDOW // CHUNK - 1)]
         p.context = [int(t) for t in rng.integers(1000, 40000, context_tokens)]
         pols.append(p)
+    return pols
+
+
+def _seam_summary(B, mode, n_ticks, warm_ticks, lat, lag, aborted, errors, stats, wall, extra):
+    L = lat[:, warm_ticks:].reshape(-1)
+    G = lag[:, warm_ticks:]
+    third = max(1, n_ticks // 3)
+    lag_first, lag_last = float(G[:, :third].mean()), float(G[:, -third:].mean())
+    p95 = float(np.percentile(L, 95))
+    ok = (not errors) and (not aborted) and p95 < CHUNK_S and lag_last < 0.1 + lag_first and float(G[:, -1].max()) < CHUNK_S
+    out = dict(streams=B, ok=bool(ok), aborted=bool(aborted), mode=mode, ticks=n_ticks, p50_latency_s=float(np.percentile(L, 50)),
+               p95_latency_s=p95, max_latency_s=float(L.max()), start_lag_first_third_s=lag_first,
+               start_lag_last_third_s=lag_last, wall_s=wall, errors=errors[:3],
+               mean_prefix_tokens=float(np.mean(stats["prefix"])) if stats["prefix"] else 0.0,
+               mean_decode_iterations=float(np.mean(stats["iters"])) if stats["iters"] else 0.0, stops=stats["stops"])
+    out.update(extra)
+    return out
+
+
+def seam_probe(eng, B, n_ticks, warm_ticks, rng, mode="cohort", context_tokens=300):
+    """Real-time paced load through the policy seam: stream i's chunk k ARRIVES (host buffer) at t0 + phase_i + k * 0.5 s,
+    phases spread uniformly over the chunk period; latency = arrival -> infer() returned.
+    mode "cohort":  one scheduler thread; the streams whose chunk has arrived form a cohort, `cohort.CohortRunner` advances
+                    their policies in lockstep, every round one batched engine call (no thread per stream).
+    mode "threads": one OS thread per stream calling the blocking per-session API through `batching.BatchingEngine`
+                    (WhisperLiveKit's own calling convention, audio_processor.py:543-551).
+    -> dict(ok, p50/p95/max latency, start lag, policy statistics)"""
+    if mode == "threads":
+        return seam_probe_threads(eng, B, n_ticks, warm_ticks, rng, context_tokens)
+    from whisperlivekit_b200.cohort import CohortRunner
+    pols = _seam_policies(eng, eng, B, rng, context_tokens)
+    runner = CohortRunner(eng, max_batch=eng.max_batch)
     chunks = (0.05 * rng.standard_normal((8, CHUNK))).astype(np.float32)
-    phases = (np.arange(B) / B * CHUNK_S) if phase_mode == "staggered" else np.zeros(B)
+    phases = np.arange(B) / B * CHUNK_S
     total = warm_ticks + n_ticks
-    lat = np.zeros((B, total)); lag = np.zeros((B, total))
+    lat = np.full((B, total), 10.0); lag = np.full((B, total), 10.0)
+    nxt = np.zeros(B, np.int64)                                              # next chunk index of every stream
+    stats = dict(prefix=[], iters=[], stops={})
+    errors, aborted = [], False
+    t_start = time.perf_counter() + 0.2
+    try:
+        while (nxt < total).any():
+            now = time.perf_counter()
+            arrival = t_start + phases + nxt * CHUNK_S
+            due = np.nonzero((nxt < total) & (arrival <= now))[0]
+            if len(due) == 0:
+                time.sleep(max(0.0, float(arrival[nxt < total].min() - now)))
+                continue
+            t0 = time.perf_counter()
+            if (nxt[due] >= warm_ticks).any() and float((t0 - arrival[due]).max()) > 2.0:
+                aborted = True                                               # the backlog ran away: this B has failed
+                break
+            for i in due:
+                pols[i].insert_audio(chunks[(i + nxt[i]) % 8])               # H2D of the chunk + window slide
+            traces = runner.run([pols[i] for i in due])
+            t1 = time.perf_counter()
+            for i, tr in zip(due, traces):
+                k = nxt[i]
+                lat[i, k] = t1 - arrival[i]; lag[i, k] = t0 - arrival[i]
+                if k >= warm_ticks:
+                    stats["prefix"].append(tr.prefix_len); stats["iters"].append(len(tr.step_tokens))
+                    stats["stops"][tr.stop] = stats["stops"].get(tr.stop, 0) + 1
+                nxt[i] += 1
+    except Exception as e:                                                   # noqa: BLE001
+        errors.append(repr(e))
+    wall = time.perf_counter() - t_start
+    rs = runner.stats
+    for p in pols:
+        p.close()
+    return _seam_summary(B, "cohort", n_ticks, warm_ticks, lat, lag, aborted, errors, stats, wall,
+                         dict(engine_calls=rs["calls"], mean_sessions_per_call=rs["sessions"] / max(1, rs["calls"]),
+                              cohorts=rs["cohorts"], mean_cohort=rs["cohort_sessions"] / max(1, rs["cohorts"])))
+
+
+def seam_probe_threads(eng, B, n_ticks, warm_ticks, rng, context_tokens=300):
+    from whisperlivekit_b200.batching import BatchingEngine
+    beng = BatchingEngine(eng, max_batch=eng.max_batch, max_wait_s=0.004)
+    pols = _seam_policies(beng, eng, B, rng, context_tokens)
+    chunks = (0.05 * rng.standard_normal((8, CHUNK))).astype(np.float32)
+    phases = np.arange(B) / B * CHUNK_S
+    total = warm_ticks + n_ticks
+    lat = np.full((B, total), 10.0); lag = np.full((B, total), 10.0)
     stats = dict(prefix=[], iters=[], stops={})
     slock = threading.Lock()
     errors = []
@@ -232,7 +305,6 @@ def seam_probe(eng, B, n_ticks, warm_ticks, rng, phase_mode="staggered", context
         try:
             for k in range(total):
                 if abort.is_set():
-                    lat[i, k:] = 10.0; lag[i, k:] = 10.0
                     return
                 due = t_start + ph + k * CHUNK_S
                 now = time.perf_counter()
@@ -241,6 +313,7 @@ def seam_probe(eng, B, n_ticks, warm_ticks, rng, phase_mode="staggered", context
                 t0 = time.perf_counter()
                 if k >= warm_ticks and t0 - due > 2.0:
                     abort.set()
+                    return
                 p.insert_audio(chunks[(i + k) % 8])                      # H2D of the chunk + window slide
                 tr = p.infer()
                 t1 = time.perf_counter()
@@ -263,23 +336,13 @@ def seam_probe(eng, B, n_ticks, warm_ticks, rng, phase_mode="staggered", context
     for p in pols:
         p.close()
     beng.close()
-    L = lat[:, warm_ticks:].reshape(-1)
-    G = lag[:, warm_ticks:]
-    third = max(1, n_ticks // 3)
-    lag_first, lag_last = float(G[:, :third].mean()), float(G[:, -third:].mean())
-    p95 = float(np.percentile(L, 95))
-    ok = (not errors) and (not abort.is_set()) and p95 < CHUNK_S and lag_last < 0.1 + lag_first and float(G[:, -1].max()) < CHUNK_S
-    return dict(streams=B, ok=bool(ok), aborted=abort.is_set(), phase=phase_mode, ticks=n_ticks, p50_latency_s=float(np.percentile(L, 50)),
-                p95_latency_s=p95, max_latency_s=float(L.max()), start_lag_first_third_s=lag_first,
-                start_lag_last_third_s=lag_last, wall_s=wall, errors=errors[:3],
-                mean_prefix_tokens=float(np.mean(stats["prefix"])) if stats["prefix"] else 0.0,
-                mean_decode_iterations=float(np.mean(stats["iters"])) if stats["iters"] else 0.0, stops=stats["stops"],
-                engine_calls=bst["calls"], mean_sessions_per_call=bst["sessions"] / max(1, bst["calls"]),
-                max_sessions_in_call=bst["max_sessions_in_call"], cohorts=bst["cohorts"],
-                mean_cohort=bst["cohort_sessions"] / max(1, bst["cohorts"]), max_cohort=bst["max_cohort"])
+    return _seam_summary(B, "threads", n_ticks, warm_ticks, lat, lag, abort.is_set(), errors, stats, wall,
+                         dict(engine_calls=bst["calls"], mean_sessions_per_call=bst["sessions"] / max(1, bst["calls"]),
+                              cohorts=bst["cohorts"], mean_cohort=bst["cohort_sessions"] / max(1, bst["cohorts"]),
+                              max_cohort=bst["max_cohort"]))
 
 
-def seam_search(eng, B0, Bmax, world, rng, n_ticks, warm_ticks):
+def seam_search(eng, B0, Bmax, world, rng, n_ticks, warm_ticks, mode="cohort"):
     """Probe B0, then walk up (pass) or down (fail) in steps of 16: at most three probes.  All ranks probe the same B
     at the same time and a probe passes only if it passes on every rank."""
     import torch
@@ -288,7 +351,7 @@ def seam_search(eng, B0, Bmax, world, rng, n_ticks, warm_ticks):
     def probe(B):
         if world > 1:
             dist.barrier()
-        r = seam_probe(eng, B, n_ticks, warm_ticks, rng)
+        r = seam_probe(eng, B, n_ticks, warm_ticks, rng, mode=mode)
         ok = r["ok"]
         if world > 1:
             t = torch.tensor([1 if ok else 0], device="cuda")
@@ -463,6 +526,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip exact_mode and other_configs")
     ap.add_argument("--no-seam", action="store_true", help="skip the real-time paced run through the seam")
     ap.add_argument("--seam-ticks", type=int, default=16)
+    ap.add_argument("--seam-mode", default="cohort", choices=["cohort", "threads"])
+    ap.add_argument("--seam-streams", type=int, default=0, help="first stream count probed through the seam (default: 2/3 of --streams)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -638,7 +703,8 @@ def main():
     note(f"scripted tick: {r['ms_dev'] / args.steps:.1f} ms device-resident, {r['ms_io'] / args.steps:.1f} ms with host chunks")
     seam_best, seam_probes = None, []
     if not args.no_seam:
-        seam_best, seam_probes = seam_search(eng, B, seam_bmax, world, rng, args.seam_ticks, 4)
+        b0 = args.seam_streams or max(16, (2 * B // 3) // 16 * 16)
+        seam_best, seam_probes = seam_search(eng, b0, seam_bmax, world, rng, args.seam_ticks, 6, mode=args.seam_mode)
         note("seam probes: " + json.dumps(seam_probes))
     la64 = None
     if not args.no_extras and args.precision == "bf16" and rank == 0 and world == 1 and max(B, seam_bmax) >= 64:
@@ -690,8 +756,10 @@ def main():
             e2e = dict(value=float(seam_best["streams"] * world), unit=UNIT,
                        h2d_bytes_per_step=seam_best["streams"] * world * CHUNK * 4,
                        d2h_bytes_per_step=int(seam_best["streams"] * world * 16 * (seam_best["mean_decode_iterations"] + 1)),
-                       how="largest probed B per GPU with p95(chunk arrival -> infer() returned) < 0.5 s and no backlog growth; "
-                           "B StreamingAlignAtt policies on B threads over BatchingEngine, real-time paced, staggered phases",
+                       how="largest probed B per GPU with p95(chunk arrival -> infer() returned) < 0.5 s and no backlog growth; B "
+                           "StreamingAlignAtt policies fed host chunks at real time with staggered phases, " +
+                           ("advanced in cohorts by one scheduler thread (cohort.CohortRunner), one batched engine call per round"
+                            if args.seam_mode == "cohort" else "one OS thread per stream over batching.BatchingEngine"),
                        best=seam_best, probes=[dict(streams=p["streams"], ok=p["ok_all_ranks"], p95_latency_s=p["p95_latency_s"],
                                                     start_lag_last_third_s=p["start_lag_last_third_s"]) for p in seam_probes],
                        scripted_with_io=scripted_io)

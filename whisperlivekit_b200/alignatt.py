@@ -203,8 +203,33 @@ class StreamingAlignAtt:
             self.engine.end_iter()
 
     def _infer(self, is_last: bool = False) -> InferTrace:
-        """reference align_att_base.py:174-322 (control flow), one engine call per hook."""
-        eng, sid, cfg = self.engine, self.sid, self.cfg
+        """Run the iteration against this policy's own engine, one call per request."""
+        eng, sid = self.engine, self.sid
+        gen = self.infer_steps(is_last)
+        try:
+            req = next(gen)
+            while True:
+                op = req[0]
+                if op == "encode":
+                    res = eng.encode([sid])[0]
+                elif op == "decode":
+                    res = eng.decode([sid], [req[1]], sot_index=self.sot_index)
+                elif op == "no_speech":
+                    res = eng.no_speech_prob([sid])[0]
+                else:                             # "select"
+                    res = engine_select(eng, [sid], self.suppress_tokens, [self.sp.blank, self.sp.eot], [req[1]], [req[2]],
+                                        window_iters=16)[0]
+                req = gen.send(res)
+        except StopIteration as stop:
+            return stop.value
+
+    def infer_steps(self, is_last: bool = False):
+        """reference align_att_base.py:174-322 (control flow) as a generator: every engine request of the iteration is
+        yielded -- ("encode",) -> content_mel_len; ("decode", tokens) -> None; ("no_speech",) -> probability;
+        ("select", first_iteration, dry_bias_pairs) -> (token, logprob, frame) -- and the InferTrace is the return
+        value.  ``_infer`` serves the requests one by one; ``cohort.CohortRunner`` advances many policies in lockstep
+        and serves each round of requests with ONE batched engine call, without a thread per stream."""
+        cfg = self.cfg
         tr = InferTrace()
         if len(self.segments) == 0:
             tr.stop = "no_segments"
@@ -213,7 +238,7 @@ class StreamingAlignAtt:
             tr.stop = "minseglen"
             return tr
 
-        content_mel_len = eng.encode([sid])[0]                               # _encode
+        content_mel_len = yield ("encode",)                                  # _encode
         tr.content_mel_len = content_mel_len
         self.trim_context()
         current_tokens = self._current_tokens()
@@ -226,7 +251,6 @@ class StreamingAlignAtt:
         audio_duration_s = self.segments_len()
         max_tokens = max(50, int(audio_duration_s * 15 * 1.5))
         tokens_produced = 0
-        iters = 0
 
         while not completed and len(current_tokens) < self.max_text_len:
             tokens_produced += 1
@@ -235,10 +259,9 @@ class StreamingAlignAtt:
                 tr.stop = "loop_detection"
                 break
             feed = current_tokens if new_segment else current_tokens[-1:]
-            eng.decode([sid], [feed], sot_index=self.sot_index)              # _get_logits_and_cross_attn
-            iters += 1
+            yield ("decode", list(feed))                                     # _get_logits_and_cross_attn
             if new_segment:
-                p = eng.no_speech_prob([sid])[0]                             # _check_no_speech
+                p = yield ("no_speech",)                                     # _check_no_speech
                 tr.no_speech_prob = p
                 if p > cfg.nonspeech_prob:
                     tr.no_speech = True
@@ -249,8 +272,7 @@ class StreamingAlignAtt:
             pen = dry_penalties(current_tokens, self.sp.eot) if cfg.dry_penalty else []     # _apply_dry_penalty
             # _suppress_blank_tokens, _apply_token_suppression, _apply_dry_penalty, _update_tokens,
             # _process_cross_attention and _get_attended_frames: one engine call (wlk_select)
-            tok, logprob, frame = engine_select(eng, [sid], self.suppress_tokens, [self.sp.blank, self.sp.eot], [first],
-                                                [[(t, -a) for t, a in pen]], window_iters=16)[0]
+            tok, logprob, frame = yield ("select", first, [(t, -a) for t, a in pen])
             if current_tokens[-1] == self.sp.eot:                            # decoding.py:282
                 tok = self.sp.eot
             current_tokens = current_tokens + [tok]

@@ -67,10 +67,11 @@ class BatchingEngine:
     max_wait_s   how long the dispatcher holds the first request of a batch for companions
     """
 
-    def __init__(self, engine, max_batch: int = 64, max_wait_s: float = 0.002):
+    def __init__(self, engine, max_batch: int = 64, max_wait_s: float = 0.002, cohort_wait_s: float = 0.05):
         self.engine = engine
         self.max_batch = int(max_batch)
         self.max_wait_s = float(max_wait_s)
+        self.cohort_wait_s = float(cohort_wait_s)
         self._lock = threading.RLock()              # serialises every call into the wrapped engine
         self._cv = threading.Condition()
         self._pending: List[_Request] = []
@@ -187,7 +188,10 @@ class BatchingEngine:
         """Called with the condition held and at least one request pending: wait for companions of the oldest
         request, then remove and return every pending request with its key (up to max_batch sessions)."""
         first = self._pending[0]
-        deadline = first.t_submit + self.max_wait_s
+        # inside a cohort every member is about to submit (it is between two engine calls of its policy iteration, a few
+        # hundred microseconds of Python each, serialised by the GIL): wait for all of them, the short window is for
+        # callers outside any iteration
+        deadline = first.t_submit + (max(self.max_wait_s, self.cohort_wait_s) if self._cohort else self.max_wait_s)
         while not self._stop:
             same = [r for r in self._pending if r.key == first.key]
             n_sess = sum(len(r.sids) for r in same)
