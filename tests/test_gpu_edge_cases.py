@@ -139,3 +139,41 @@ def test_pcm16_ingest_equals_host_conversion(pair):
     assert eng.encode([a, b]) == [100, 100]
     assert np.array_equal(eng.read_mel(a), eng.read_mel(b))
     eng.close_session(a); eng.close_session(b)
+
+
+def test_incremental_log_mel_is_bit_identical_to_full_recompute(monkeypatch):
+    """N1, exact part: a rolling window (0.5 s in, oldest 0.5 s out, plus growth and odd-sized steps) encoded
+    incrementally -- only the ~2 leading and ~50 trailing frames are transformed, the rest of the raw log-mel is moved --
+    gives bit-identical mel and encoder output to a session that recomputes every frame (fresh session, same audio)."""
+    from whisperlivekit_b200.dims import DIMS
+    from whisperlivekit_b200.engine import WhisperEngine
+    from whisperlivekit_b200.weights import synthetic_audio, synthetic_state_dict
+    dims = DIMS["micro"]
+    sd = synthetic_state_dict(dims, seed=11)
+    heads = [(0, 1), (1, 0), (1, 1)]
+    eng = WhisperEngine(dims, sd, heads, precision="fp32", max_sessions=2, max_batch=2)
+    audio = synthetic_audio(40.0, seed=77)
+    s = eng.open_session()
+    window = np.zeros(0, np.float32)
+    pos = 0
+    # (append samples, drop samples): growth, steady 0.5 s slides at the 30 s cap, a slide that is not a whole number of
+    # frames (falls back to a full pass), a pure append, a big drop
+    plan = [(160000, 0), (8000, 0), (320000 - 8000, 0), (8000, 8000), (8000, 8000), (8000, 8000), (5000, 5001), (3000, 0),
+            (8000, 8000), (16000, 100000), (8000, 8000)]
+    for k, (app, drop) in enumerate(plan):
+        seg = audio[pos: pos + app]; pos += app
+        eng.append_audio(s, seg)
+        window = np.concatenate([window, seg])
+        if drop:
+            eng.drop_audio(s, drop)
+            window = window[drop:]
+        c = eng.encode([s])[0]
+        mel_inc, enc_inc = eng.read_mel(s), eng.read_encoder(s)
+        f = eng.open_session()                                  # fresh session: full pass over the same window
+        eng.append_audio(f, window)
+        assert eng.encode([f])[0] == c
+        mel_full, enc_full = eng.read_mel(f), eng.read_encoder(f)
+        eng.close_session(f)
+        assert np.array_equal(mel_inc, mel_full), (k, np.abs(mel_inc - mel_full).max())
+        assert np.array_equal(enc_inc, enc_full), k
+    eng.close()

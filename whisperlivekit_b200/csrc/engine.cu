@@ -63,6 +63,9 @@ struct Session {
     bool open = false;
     float* audio = nullptr; int64_t audio_len = 0;
     float* mel_raw = nullptr; float* mel_blockmax = nullptr;
+    // incremental log-mel: mel_raw holds the raw log-mel of the window as it was when audio_len was mel_n, minus
+    // mel_dropped samples dropped at the front since (-1: nothing cached)
+    int64_t mel_n = -1, mel_dropped = 0;
     void* xa = nullptr; void* cross_kv = nullptr; void* self_kv = nullptr;
     float* align = nullptr; float* logits_last = nullptr; float* logits_sot = nullptr;
     float* attn_out = nullptr; float* stats = nullptr;
@@ -94,6 +97,7 @@ struct wlk_engine {
     // token-step CUDA graphs: the ~390 launches of one decoder step depend only on the batch size (every per-session
     // quantity travels in the staged job arrays), so they are captured once per batch size and replayed
     bool graphs_on = true;
+    bool mel_incremental = true;      // WLK_MEL_INCREMENTAL=0: recompute every frame of the window at every encode
     struct GraphSlot { cudaGraphExec_t exec; uint64_t last_use; };
     std::map<uint64_t, GraphSlot> dec_graphs;     // LRU-bounded: under the batching shim the batch size varies in 1..max_batch
     std::set<uint64_t> dec_graph_seen;
@@ -494,6 +498,29 @@ void encode_batch(wlk_engine* e, const int32_t* sids, int n, int32_t* content_ou
         mj[i].audio = s.audio; mj[i].raw = s.mel_raw; mj[i].blockmax = s.mel_blockmax;
         mj[i].out = offs(e->mel_t, (size_t)i * MEL_ROWS * nm, es);
         mj[i].n = (int32_t)N; mj[i].n_compute = (int32_t)n_compute; mj[i].n_total = (int32_t)n_total; mj[i].pad = 0;
+        mj[i].keep_lo = mj[i].keep_hi = 0;
+        // Incremental log-mel (exact).  Frame f of the window reads samples [160 f - 200, 160 f + 200).  After the window
+        // slid by d = mel_dropped / 160 whole frames and grew at the end, new frame f equals old frame f + d bit for bit
+        // as long as neither touches an edge: f >= 2 (no reflection at the new left edge; f + d >= 2 follows) and
+        // 160 f + 200 <= old end (the old pass saw the same samples, not the zero padding).  Those rows are moved, the
+        // two leading frames and the ~50 trailing ones are recomputed.
+        if (e->mel_incremental && s.mel_n >= 0 && s.mel_dropped % HOP == 0 && s.mel_dropped <= s.mel_n &&
+            n_compute <= MEL_STORE_FRAMES && (s.mel_n + 199) / HOP + 1 <= MEL_STORE_FRAMES) {
+            const int64_t d = s.mel_dropped / HOP;
+            const int64_t old_end = s.mel_n - s.mel_dropped;                   // old audio end in new coordinates
+            const int64_t lo = d == 0 ? 0 : 2;
+            int64_t hi = old_end >= 200 ? (old_end - 200) / HOP + 1 : 0;       // exclusive
+            if (hi > n_compute) hi = n_compute;
+            if (hi > lo) {
+                if (d > 0) {
+                    const size_t bytes = (size_t)(hi - lo) * nm * 4;
+                    CUDA_CHECK(cudaMemcpyAsync(e->mel_scratch, s.mel_raw + (size_t)(lo + d) * nm, bytes, cudaMemcpyDeviceToDevice, e->st));
+                    CUDA_CHECK(cudaMemcpyAsync(s.mel_raw + (size_t)lo * nm, e->mel_scratch, bytes, cudaMemcpyDeviceToDevice, e->st));
+                }
+                mj[i].keep_lo = (int32_t)lo; mj[i].keep_hi = (int32_t)hi;
+            }
+        }
+        s.mel_n = N; s.mel_dropped = 0;
         s.content_len = (int)((n_total - N_FRAMES) / 2);            // simul_whisper.py:350 (unclamped: the policy's
         content_out[i] = s.content_len;                             // frame_threshold test needs the true value)
         xkv[i] = s.cross_kv;
@@ -796,8 +823,9 @@ void alloc_session(wlk_engine* e, Session& s) {
     size_t* acct = &s.bytes;
     s.bytes = 0;
     s.audio = dmalloc<float>(e, AUDIO_CAP, acct);
-    s.mel_raw = dmalloc<float>(e, (size_t)MEL_ROWS * D.n_mels, acct);
-    s.mel_blockmax = dmalloc<float>(e, MEL_MAX_CTAS, acct);
+    s.mel_raw = dmalloc<float>(e, (size_t)MEL_STORE_FRAMES * D.n_mels, acct);
+    s.mel_blockmax = dmalloc<float>(e, MEL_MAX_CTAS + MEL_MAX_PARTS, acct);
+    s.mel_n = -1; s.mel_dropped = 0;
     s.xa = dmalloc_bytes((size_t)N_CTX * D.n_audio_state * es, acct);
     s.cross_kv = dmalloc_bytes((size_t)D.n_text_layer * 2 * N_CTX * D.n_text_state * es, acct);
     s.self_kv = dmalloc_bytes((size_t)D.n_text_layer * 2 * D.n_text_ctx * D.n_text_state * es, acct);
@@ -887,6 +915,7 @@ void create_engine(const wlk_dims* dims, const wlk_config* cfg, wlk_engine** out
     }
     CUDA_CHECK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     {   const char* v = getenv("WLK_GRAPHS"); e->graphs_on = !(v && v[0] == '0'); }
+    {   const char* v = getenv("WLK_MEL_INCREMENTAL"); e->mel_incremental = !(v && v[0] == '0'); }
     for (auto& t : e->timers) CUDA_CHECK(cudaEventCreate(&t));
     CUDA_CHECK(cudaEventCreateWithFlags(&e->stg_done, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventRecord(e->stg_done, e->st));
@@ -921,7 +950,7 @@ void create_engine(const wlk_dims* dims, const wlk_config* cfg, wlk_engine** out
     e->att = dmalloc_bytes((size_t)B * N_CTX * d * es, acct);
     e->hid = dmalloc_bytes((size_t)B * N_CTX * 4 * d * es, acct);
     e->audio_scratch = dmalloc<float>(e, AUDIO_CAP, acct);
-    e->mel_scratch = dmalloc<float>(e, (size_t)MEL_ROWS * D.n_mels, acct);
+    e->mel_scratch = dmalloc<float>(e, (size_t)MEL_STORE_FRAMES * D.n_mels, acct);
     if (e->gemm_backend == WLK_BACKEND_TCGEN05) {
         e->sk_scratch = dmalloc<float>(e, SK_SCRATCH_FLOATS, acct);
         e->sk_counters = dmalloc<int>(e, SK_MAX_TILES, acct);
@@ -1222,13 +1251,15 @@ int wlk_session_drop_audio(wlk_engine* e, int32_t sid, int64_t n) {
         CUDA_CHECK(cudaMemcpyAsync(e->audio_scratch, s.audio + n, (size_t)keep * 4, cudaMemcpyDeviceToDevice, e->st));
         CUDA_CHECK(cudaMemcpyAsync(s.audio, e->audio_scratch, (size_t)keep * 4, cudaMemcpyDeviceToDevice, e->st));
     }
+    if (s.mel_n >= 0) s.mel_dropped += n;
     s.audio_len = keep;
     WLK_API_END
 }
 int wlk_session_clear_audio(wlk_engine* e, int32_t sid) {
     WLK_API_BEGIN
     LOCK(e);
-    get_session(e, sid).audio_len = 0;
+    Session& s = get_session(e, sid);
+    s.audio_len = 0; s.mel_n = -1; s.mel_dropped = 0;
     WLK_API_END
 }
 int wlk_session_audio_len(wlk_engine* e, int32_t sid, int64_t* n) {
@@ -1275,6 +1306,7 @@ int wlk_encode_mel(wlk_engine* e, int32_t sid, const float* mel_host, int32_t co
     {   ProfScope ps(e, WLK_KC_MEL);
         mel_import(e->mel_scratch, e->mel_t, e->act, nm, e->st); }
     run_encoder(e, &sid, 1, xkv_dev);
+    s.mel_n = -1;                                    // the caller's mel: nothing of this window is cached in mel_raw
     s.content_len = content_mel_len > N_CTX ? N_CTX : content_mel_len;
     CUDA_CHECK(cudaStreamSynchronize(e->st));        // mel_host may be reused by the caller
     WLK_API_END
@@ -1466,6 +1498,10 @@ int wlk_read_mel(wlk_engine* e, int32_t sid, float* out) {
     float* scratch = e->mel_scratch;
     mj[0].audio = s.audio; mj[0].raw = s.mel_raw; mj[0].blockmax = s.mel_blockmax; mj[0].out = scratch;
     mj[0].n = (int32_t)N; mj[0].n_compute = (int32_t)n_compute; mj[0].n_total = (int32_t)((N + 480000) / HOP); mj[0].pad = 0;
+    WLK_CHECK(s.mel_n == N && s.mel_dropped == 0, "read_mel: the audio changed since the last encode");
+    // the tap shows what the encoder consumed: the session's cached raw rows (however they were produced -- moved or
+    // recomputed) go through the clamp / scale pass again; only audio longer than the stored rows is recomputed
+    mj[0].keep_lo = 0; mj[0].keep_hi = n_compute <= MEL_STORE_FRAMES ? (int32_t)n_compute : 0;
     sg.upload();
     mel_forward(mj_dev, 1, nm, e->w.filtT, e->w.window, e->w.twiddle, e->w.filt_span, DT_F32, (int)n_compute, e->st);
     float* h = tap_buffer(e, (size_t)MEL_ROWS * nm);

@@ -71,8 +71,9 @@ mel_power_kernel(const MelJob* __restrict__ jobs, int n_mels, const float* __res
     constexpr int HALF = N_FFT / 2;                  // 200
     __shared__ float2 sd[FR][HALF];                  // (s[j], d[j]); entry 0 holds (xw[0], xw[200])
     __shared__ float2 tw[N_FFT];
-    __shared__ float pw[FR][N_FREQ + 3];
+    __shared__ __align__(16) float pw[FR][N_FREQ + 3];   // first the TMA-staged samples of the CTA's frames, then the power spectra
     __shared__ float red[8];
+    __shared__ __align__(8) uint64_t stage_bar;
     const MelJob job = jobs[blockIdx.y];
     const int f0 = blockIdx.x * FR;
     const int tid = threadIdx.x;
@@ -81,8 +82,29 @@ mel_power_kernel(const MelJob* __restrict__ jobs, int n_mels, const float* __res
         if (tid == 0) job.blockmax[blockIdx.x] = -10.0f;
         return;
     }
+    if (f0 >= job.keep_lo && f0 + FR <= job.keep_hi) return;       // incremental: these rows of `raw` are still this window's
+    // The samples the CTA's 16 frames touch are one contiguous run of (FR - 1) * HOP + N_FFT = 2800 floats.  Away from the
+    // edges of the audio it is staged into shared memory by one bulk copy of the TMA engine (cp.async.bulk, completion
+    // on an mbarrier) instead of 2800 strided per-thread loads; edge CTAs (reflection, zero padding) gather per sample.
+    constexpr int SPAN = (FR - 1) * HOP + N_FFT;
+    static_assert(SPAN <= FR * (N_FREQ + 3) && (SPAN * 4) % 16 == 0, "sample staging aliases pw");
+    const int s_begin = f0 * HOP - HALF;
+    const bool staged = s_begin >= 0 && s_begin + SPAN <= job.n && ((reinterpret_cast<uintptr_t>(job.audio + s_begin) & 15) == 0);
+    float* stage = &pw[0][0];
+    if (staged) {
+        const uint32_t bar = ptx::smem_u32(&stage_bar);
+        if (tid == 0) {
+            ptx::mbar_init(bar, 1);
+            ptx::fence_barrier_init();
+            ptx::mbar_arrive_expect_tx(bar, SPAN * 4);
+            ptx::tma_load_1d(ptx::smem_u32(stage), job.audio + s_begin, SPAN * 4, bar);
+        }
+        __syncthreads();
+        ptx::mbar_wait(bar, 0);
+    }
     for (int i = tid; i < N_FFT; i += 224) tw[i] = twiddle[i];
     auto sample = [&](int fr, int j) -> float {         // windowed sample j of frame fr
+        if (staged) return stage[fr * HOP + j] * window[j];
         int s = (f0 + fr) * HOP - HALF + j;             // torch.stft(center=True): reflect pad n_fft/2
         if (s < 0) s = -s;
         if (job.pad && s >= job.n) s = 2 * (job.n - 1) - s;  // streaming window: reflect at the right edge too
@@ -152,7 +174,10 @@ mel_finalize_kernel(const MelJob* __restrict__ jobs, int n_mels) {
     float m = -10.0f;    // frames inside the zero padding contribute log10(1e-10)
     const int n_valid = min(job.n_compute, job.n_total);
     const int n_ctas = (n_valid + MEL_FRAMES_PER_CTA - 1) / MEL_FRAMES_PER_CTA;
-    for (int i = threadIdx.x; i < n_ctas; i += 256) m = fmaxf(m, job.blockmax[i]);
+    // stored rows: the partial maxima of mel_max_kernel (they cover kept and recomputed rows alike); frames past the
+    // stored rows (audio longer than 30 s: always a full pass) only exist as the per-CTA maxima of this pass
+    if (threadIdx.x < MEL_MAX_PARTS) m = fmaxf(m, job.blockmax[MEL_MAX_CTAS + threadIdx.x]);
+    for (int i = MEL_STORE_FRAMES / MEL_FRAMES_PER_CTA + threadIdx.x; i < n_ctas; i += 256) m = fmaxf(m, job.blockmax[i]);
     const float gmax = block_max_all<256>(m, red);
     const float thr = gmax - 8.0f;
     TO* out = reinterpret_cast<TO*>(job.out);
@@ -169,6 +194,23 @@ mel_finalize_kernel(const MelJob* __restrict__ jobs, int n_mels) {
     }
 }
 
+// partial maxima over the stored raw rows of every job: blockmax[MEL_MAX_CTAS + p], p < MEL_MAX_PARTS
+__global__ void __launch_bounds__(256)
+mel_max_kernel(const MelJob* __restrict__ jobs, int n_mels) {
+    __shared__ float red[8];
+    const MelJob job = jobs[blockIdx.y];
+    const int n_rows = min(min(job.n_compute, job.n_total), MEL_STORE_FRAMES);
+    const int64_t total4 = (int64_t)n_rows * n_mels / 4;                  // n_mels % 8 == 0
+    const float4* r4 = reinterpret_cast<const float4*>(job.raw);
+    float m = -INFINITY;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total4; i += (int64_t)MEL_MAX_PARTS * 256) {
+        const float4 v = r4[i];
+        m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
+    m = block_max<256>(m, red);
+    if (threadIdx.x == 0) job.blockmax[MEL_MAX_CTAS + blockIdx.x] = m;
+}
+
 void mel_forward(const MelJob* jobs_dev, int batch, int n_mels, const float* filtT, const float* window,
                  const float2* twiddle, const int2* filt_span, int out_type, int max_frames, cudaStream_t st) {
     int ctas = (max_frames + MEL_FRAMES_PER_CTA - 1) / MEL_FRAMES_PER_CTA;
@@ -176,6 +218,8 @@ void mel_forward(const MelJob* jobs_dev, int batch, int n_mels, const float* fil
     if (ctas > MEL_MAX_CTAS) ctas = MEL_MAX_CTAS;
     dim3 g1(ctas, batch);
     mel_power_kernel<<<g1, 224, 0, st>>>(jobs_dev, n_mels, filtT, window, twiddle, filt_span);
+    CUDA_CHECK(cudaGetLastError());
+    mel_max_kernel<<<dim3(MEL_MAX_PARTS, batch), 256, 0, st>>>(jobs_dev, n_mels);
     CUDA_CHECK(cudaGetLastError());
     dim3 g2(64, batch);
     if (out_type == DT_F32) mel_finalize_kernel<float><<<g2, 256, 0, st>>>(jobs_dev, n_mels);

@@ -13,14 +13,16 @@ constexpr int N_FREQ = 201;
 constexpr int N_FFT = 400;
 constexpr int HOP = 160;
 constexpr int MEL_FRAMES_PER_CTA = 16;
-constexpr int MEL_STORE_FRAMES = N_FRAMES + 2;          // rows of MelJob.raw
+constexpr int MEL_STORE_FRAMES = 3008;                  // rows of MelJob.raw (N_FRAMES + 2, rounded up to whole CTAs)
+constexpr int MEL_MAX_PARTS = 8;                        // partial maxima over the stored rows (mel_max_kernel)
 constexpr int MEL_MAX_FRAMES = 2 * N_FRAMES + 2;        // a session may buffer up to 60 s: every frame joins the global max
 constexpr int MEL_MAX_CTAS = (MEL_MAX_FRAMES + MEL_FRAMES_PER_CTA - 1) / MEL_FRAMES_PER_CTA;   // 376
 
 struct MelJob {                 // one per session in the batch (device array)
     const float* audio;         // device, n samples
     float* raw;                 // [MEL_STORE_FRAMES][n_mels] fp32 log10(max(mel,1e-10)) for frames < min(n_compute, MEL_STORE_FRAMES)
-    float* blockmax;            // [MEL_MAX_CTAS]
+    float* blockmax;            // [MEL_MAX_CTAS + MEL_MAX_PARTS]: per-CTA maxima of the frames computed in this pass, then
+                                // the partial maxima over ALL stored rows (kept + recomputed)
     void* out;                  // [MEL_ROWS][n_mels] activation type, time-major, zero pad rows
     int32_t n;                  // samples
     int32_t n_compute;          // frames whose window touches audio (others are the silence constant); frames past
@@ -28,6 +30,9 @@ struct MelJob {                 // one per session in the batch (device array)
                                 // padded spectrogram, before pad_or_trim cuts it to 3000 frames)
     int32_t n_total;            // floor((n + 480000) / 160): frames the reference's STFT keeps
     int32_t pad;
+    // incremental log-mel: rows [keep_lo, keep_hi) of `raw` already hold this window's values (same samples, same
+    // arithmetic as a full pass: bit-identical) and are not recomputed
+    int32_t keep_lo, keep_hi;
 };
 
 // max_frames: the largest n_compute in the batch (sizes the grid)

@@ -83,6 +83,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
         : "memory");
 }
 
+// 1D bulk copy global -> shared through the TMA engine (16-byte aligned addresses, size a multiple of 16)
+__device__ __forceinline__ void tma_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar)
+        : "memory");
+}
+
 // ---- TMEM -----------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_result, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "r"(ncols)

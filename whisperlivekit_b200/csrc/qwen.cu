@@ -671,8 +671,8 @@ void append_audio(wlk_qwen* q, const int32_t* sids, int n, const float* pcm, con
         for (int j = 0; j < i; ++j) WLK_CHECK(sids[j] != sids[i], "session %d appears twice in the batch", sids[i]);
         if (!s.audio) {
             CUDA_CHECK(cudaMalloc(&s.audio, (size_t)QMEL_AUDIO_CAP * 4));
-            CUDA_CHECK(cudaMalloc(&s.mel_raw, (size_t)(QMEL_MAX_FRAMES + 2) * D.n_mels * 4));
-            CUDA_CHECK(cudaMalloc(&s.mel_blockmax, (size_t)MEL_MAX_CTAS * 4));
+            CUDA_CHECK(cudaMalloc(&s.mel_raw, (size_t)MEL_STORE_FRAMES * D.n_mels * 4));
+            CUDA_CHECK(cudaMalloc(&s.mel_blockmax, (size_t)(MEL_MAX_CTAS + MEL_MAX_PARTS) * 4));
             q->bytes_sessions += (size_t)QMEL_AUDIO_CAP * 4 + (size_t)(QMEL_MAX_FRAMES + 2) * D.n_mels * 4 + MEL_MAX_CTAS * 4;
         }
         int64_t upto;
