@@ -46,8 +46,8 @@ import numpy as np
 CHUNK_S = 0.5
 CHUNK = 8000
 WINDOW = 480000
-PREFIX = 48
-STEPS_PER_CHUNK = 8
+PREFIX = int(os.environ.get("WLK_BENCH_PREFIX", "48"))            # the headline workload: 48 + 8 (overrides are for experiments)
+STEPS_PER_CHUNK = int(os.environ.get("WLK_BENCH_STEPS", "8"))
 UNIT = "concurrent real-time streams (audio-s per wall-s)"
 CONFIGS = ["alignatt-large-v3", "alignatt-base-en-1stream", "localagreement-large-v3-64", "qwen-tower-128"]
 

@@ -352,3 +352,46 @@ def test_fused_select_equals_elementary_calls():
     for a, b in zip(*results):
         assert a[0] == b[0]
         assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+def test_bf16_long_prefill_self_attention_on_tensor_cores():
+    """A context-saturated prefix (the reference keeps up to n_text_ctx - 20 tokens, align_att_base.py:100-113): the causal
+    decoder self-attention of a 300-token prefill runs on the tensor cores (attn_tc_kernel<MODE_SELF>) in bf16 mode; ragged
+    batch, then a second multi-token call that continues at a non-zero cache offset, then token steps.  Against the SIMT
+    kernels of the same precision mode and against the CPU oracle."""
+    from oracle import whisper_oracle as wo
+    from whisperlivekit_b200.engine import WhisperEngine
+    for k in list(_ENGINES):
+        _ENGINES.pop(k).close()
+    g, dims, sd, audio, heads = case_setup("tiny")
+    rng = np.random.default_rng(8)
+    base = list(g["forced_prefix"])
+    p0 = base + [int(t) for t in rng.integers(1000, 30000, 300 - len(base))]
+    p1 = base + [int(t) for t in rng.integers(1000, 30000, 170 - len(base))]
+    more0 = [int(t) for t in rng.integers(1000, 30000, 20)]
+    more1 = [int(t) for t in rng.integers(1000, 30000, 17)]
+    outs = {}
+    for backend in ("tcgen05", "simt"):
+        eng = WhisperEngine(dims, sd, heads, precision="bf16", max_sessions=2, max_batch=2, attn_backend=backend)
+        s0, s1 = eng.open_session(), eng.open_session()
+        eng.append_audio(s0, audio); eng.append_audio(s1, audio[:40000])
+        eng.encode([s0, s1])
+        eng.decode([s0, s1], [p0, p1])
+        a = (eng.read_logits(s0), eng.read_logits(s1))
+        eng.decode([s0, s1], [more0, more1])                       # >= 16 rows again, cache offsets 300 / 170
+        b = (eng.read_logits(s0), eng.read_logits(s1))
+        eng.decode([s0, s1], [[1169], [2068]])
+        c = (eng.read_logits(s0), eng.read_logits(s1), eng.greedy_and_align([s0, s1]))
+        outs[backend] = (a, b, c)
+        eng.close()
+    orc = wo.OracleEngine(dims, sd, heads)
+    so = orc.open_session()
+    orc.append_audio(so, audio); orc.encode([so]); orc.decode([so], [p0]); ref_a = orc.read_logits(so)
+    orc.decode([so], [more0]); ref_b = orc.read_logits(so)
+    orc.decode([so], [[1169]]); ref_c = orc.read_logits(so)
+    for stage in range(3):
+        for i in (0, 1):
+            assert np.abs(outs["tcgen05"][stage][i] - outs["simt"][stage][i]).max() < 6e-2, (stage, i)
+    for stage, ref in enumerate((ref_a, ref_b, ref_c)):
+        assert np.abs(outs["tcgen05"][stage][0] - ref).max() < 1e-1, stage
+        assert np.abs(outs["simt"][stage][0] - ref).max() < 1e-1, stage

@@ -87,18 +87,26 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
         : "memory");
 }
 
-// CROSS = false: encoder self-attention, Q/K/V tiles all come out of the fused qkv buffer (tensor map `tm`).
-// CROSS = true : decoder cross-attention of a prefill (many query rows per session): Q tiles from the packed
-//                query buffer (`tm`), K/V tiles from the session's head-major cross-K/V planes through a
-//                per-session tensor map kept in global memory (`kv_maps[job.slot]`).  Alignment heads are
-//                skipped here: their rows need the exactly normalised probabilities exported, which the
-//                SIMT kernel produces.
-template <bool CROSS, bool X3>
+// MODE 0: encoder self-attention, Q/K/V tiles all come out of the fused qkv buffer (tensor map `tm`).
+// MODE 1: decoder cross-attention of a prefill (many query rows per session): Q tiles from the packed
+//         query buffer (`tm`), K/V tiles from the session's head-major cross-K/V planes through a
+//         per-session tensor map kept in global memory (`kv_maps[job.slot]`).  Alignment heads are
+//         skipped here: their rows need the exactly normalised probabilities exported, which the
+//         SIMT kernel produces.
+// MODE 2: decoder SELF-attention of a prefill, causal: Q as in mode 1, K/V tiles from the session's self-K/V
+//         cache planes [L][2][H][n_text_ctx][64] (per-session tensor map); query row at position p sees keys
+//         0..p -- the mask is applied per row where the probabilities are formed (masked keys get exactly 0),
+//         and only the key tiles up to the tile's last position are visited.  A long context prefix (the
+//         reference keeps up to n_text_ctx - 20 = 428 tokens, align_att_base.py:100-113) costs ~90 k query
+//         rows x 32 layers per tick at 48 streams: on the SIMT kernel that was half of the tick.
+constexpr int MODE_ENC = 0, MODE_CROSS = 1, MODE_SELF = 2;
+template <int MODE, bool X3>
 __global__ void __launch_bounds__(ATT_THREADS, X3 ? 1 : 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_lo,
                const CUtensorMap* __restrict__ kv_maps,
                const DecJob* __restrict__ jobs, int layer, const int32_t* __restrict__ align_rank,
-               int n_head, int d_model, void* __restrict__ out_ptr) {
+               int n_head, int d_model, int kv_len, void* __restrict__ out_ptr) {
+    constexpr bool CROSS = MODE != MODE_ENC;              // Q from the packed query buffer, K/V through a per-session map
     static_assert(!(CROSS && X3), "the split-operand variant serves the encoder only");
     using AL = AttLayout<X3>;
     constexpr uint32_t SM_Q = AL::SM_Q, SM_K = AL::SM_K, SM_V = AL::SM_V, SM_BAR = AL::SM_BAR, SM_XCH = AL::SM_XCH;
@@ -120,19 +128,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ C
     ptx::griddep_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
-    constexpr int NT = (N_CTX + BKV - 1) / BKV;          // 12 key tiles
+    int NT = (N_CTX + BKV - 1) / BKV;                    // 12 key tiles (encoder, cross)
+    int pos0 = 0;                                        // MODE_SELF: position of the tile's first query row
     // tile origins (tensor-map coordinates) and the number of query rows this CTA owns
     const CUtensorMap* tm_kv = &tm;
     int q_row, q_col = h * DH, k_row, k_col, v_row, v_col, out_row, n_q;
     if constexpr (CROSS) {
         const DecJob job = jobs[b];
-        if (q0 >= job.n_rows || align_rank[layer * n_head + h] >= 0) return;     // uniform: before any barrier / TMEM use
+        if (q0 >= job.n_rows) return;                                            // uniform: before any barrier / TMEM use
+        if (MODE == MODE_CROSS && align_rank[layer * n_head + h] >= 0) return;
         tm_kv = kv_maps + job.slot;
         q_row = job.row_off + q0;
-        k_row = (((layer * 2 + 0) * n_head) + h) * N_CTX; k_col = 0;
-        v_row = (((layer * 2 + 1) * n_head) + h) * N_CTX; v_col = 0;
+        k_row = (((layer * 2 + 0) * n_head) + h) * kv_len; k_col = 0;
+        v_row = (((layer * 2 + 1) * n_head) + h) * kv_len; v_col = 0;
         out_row = job.row_off + q0;
         n_q = min(BQ, job.n_rows - q0);
+        if (MODE == MODE_SELF) {
+            pos0 = job.offset + q0;
+            NT = (pos0 + n_q + BKV - 1) / BKV;                                   // keys 0 .. position of the last row
+        }
     } else {
         q_row = b * N_CTX + q0;
         k_row = b * N_CTX; k_col = d_model + h * DH;
@@ -255,7 +269,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ C
         // (MASKED only for the last, 92-key tile) and exp2 is a bare MUFU.
         auto tile = [&](int j, auto masked_tag) {
             constexpr bool MASKED = decltype(masked_tag)::value;
-            const int n_valid = N_CTX - j * BKV - half * (BKV / 2);   // valid keys in this thread's 64 (MASKED only)
+            // valid keys among this thread's 64 (MASKED only): the tail of the 1500 frames, or -- causal -- keys up to
+            // the row's own position
+            const int n_valid = MODE == MODE_SELF ? (pos0 + r + 1) - j * BKV - half * (BKV / 2)
+                                                  : N_CTX - j * BKV - half * (BKV / 2);
             ptx::mbar_wait(bar_s_full, j & 1);
             ptx::tc_fence_after();                            // (Q K^T of tile j retired => P V of tile j-1 did too)
             uint32_t va[16], vb[16];
@@ -335,9 +352,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ C
             ptx::mbar_arrive(bar_s_free);     // S fully consumed: next Q K^T may overwrite it
             ptx::mbar_arrive(bar_p_full);     // P written, O rescaled if needed: P V may run
         };
+        if (MODE == MODE_SELF) {
 #pragma unroll 1
-        for (int j = 0; j < NT - 1; ++j) tile(j, std::false_type{});
-        tile(NT - 1, std::true_type{});
+            for (int j = 0; j < NT; ++j) tile(j, std::true_type{});
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < NT - 1; ++j) tile(j, std::false_type{});
+            tile(NT - 1, std::true_type{});
+        }
         ptx::mbar_wait(bar_o_full, (NT - 1) & 1);
         ptx::tc_fence_after();
         const float inv = 1.0f / (l + exchange(l));
@@ -382,9 +404,9 @@ void enc_attention_tcgen05(const void* qkv, int batch, int n_head, int d_model, 
               "qkv tensor map: %s", err.c_str());
     static bool seen[64] = {};
     if (first_on_device(seen))
-        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AttLayout<false>::SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<MODE_ENC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AttLayout<false>::SMEM));
     dim3 grid((N_CTX + BQ - 1) / BQ, n_head, batch);
-    attn_tc_kernel<false, false><<<grid, ATT_THREADS, AttLayout<false>::SMEM, st>>>(tm, tm, nullptr, nullptr, 0, nullptr, n_head, d_model, out);
+    attn_tc_kernel<MODE_ENC, false><<<grid, ATT_THREADS, AttLayout<false>::SMEM, st>>>(tm, tm, nullptr, nullptr, 0, nullptr, n_head, d_model, N_CTX, out);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -399,9 +421,9 @@ void enc_attention_tcgen05_x3(const void* qkv_hi, const void* qkv_lo, int batch,
               "qkv lo tensor map: %s", err.c_str());
     static bool seen[64] = {};
     if (first_on_device(seen))
-        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AttLayout<true>::SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<MODE_ENC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AttLayout<true>::SMEM));
     dim3 grid((N_CTX + BQ - 1) / BQ, n_head, batch);
-    attn_tc_kernel<false, true><<<grid, ATT_THREADS, AttLayout<true>::SMEM, st>>>(tm, tml, nullptr, nullptr, 0, nullptr, n_head, d_model, out);
+    attn_tc_kernel<MODE_ENC, true><<<grid, ATT_THREADS, AttLayout<true>::SMEM, st>>>(tm, tml, nullptr, nullptr, 0, nullptr, n_head, d_model, N_CTX, out);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -422,10 +444,35 @@ void dec_cross_attention_tcgen05(const void* q, int total_rows, const DecJob* jo
               "query tensor map: %s", err.c_str());
     static bool seen[64] = {};
     if (first_on_device(seen))
-        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AttLayout<false>::SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<MODE_CROSS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AttLayout<false>::SMEM));
     dim3 grid((max_rows + BQ - 1) / BQ, n_head, n_jobs);
-    CUDA_CHECK(launch_pdl(attn_tc_kernel<true, false>, grid, dim3(ATT_THREADS), (size_t)AttLayout<false>::SMEM, st, tm, tm,
-                          reinterpret_cast<const CUtensorMap*>(kv_maps_dev), jobs, layer, align_rank, n_head, d_model, out));
+    CUDA_CHECK(launch_pdl(attn_tc_kernel<MODE_CROSS, false>, grid, dim3(ATT_THREADS), (size_t)AttLayout<false>::SMEM, st, tm, tm,
+                          reinterpret_cast<const CUtensorMap*>(kv_maps_dev), jobs, layer, align_rank, n_head, d_model, N_CTX, out));
+}
+
+// tensor map over one session's self-K/V cache viewed as [L * 2 * H * n_text_ctx rows, 64] bf16
+void make_self_kv_tmap(void* tmap_out_host, const void* self_kv, int n_layer, int n_head, int n_text_ctx) {
+    std::string err;
+    WLK_CHECK(make_tmap_bf16_2d(reinterpret_cast<CUtensorMap*>(tmap_out_host), self_kv,
+                                (uint64_t)n_layer * 2 * n_head * n_text_ctx, DH, DH, BKV, DH, &err),
+              "self-K/V tensor map: %s", err.c_str());
+}
+
+// causal self-attention of a decoder prefill on the tensor cores (bf16): every head, rows [0, n_rows) of each job at
+// positions job.offset + row; the cache rows of this call were written by the QKV GEMM's scatter epilogue just before
+void dec_self_attention_tcgen05(const void* q, int total_rows, const DecJob* jobs, int n_jobs, int max_rows, int layer,
+                                int n_head, int d_model, int n_text_ctx, const void* kv_maps_dev, void* out, cudaStream_t st) {
+    CUtensorMap tm;
+    std::string err;
+    WLK_CHECK(make_tmap_bf16_2d(&tm, q, (uint64_t)total_rows, (uint64_t)d_model, (uint64_t)d_model, BQ, DH, &err),
+              "query tensor map: %s", err.c_str());
+    static bool seen[64] = {};
+    if (first_on_device(seen))
+        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<MODE_SELF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AttLayout<false>::SMEM));
+    dim3 grid((max_rows + BQ - 1) / BQ, n_head, n_jobs);
+    CUDA_CHECK(launch_pdl(attn_tc_kernel<MODE_SELF, false>, grid, dim3(ATT_THREADS), (size_t)AttLayout<false>::SMEM, st, tm, tm,
+                          reinterpret_cast<const CUtensorMap*>(kv_maps_dev), jobs, layer, (const int32_t*)nullptr, n_head, d_model,
+                          n_text_ctx, out));
 }
 
 }  // namespace wlk

@@ -113,6 +113,7 @@ struct wlk_engine {
     std::vector<int32_t> align_rank_host;     // [L*H] -> rank or -1
     int32_t* align_rank_dev = nullptr;
     uint8_t* kv_maps_dev = nullptr;           // [max_sessions] CUtensorMap (128 B each) over each session's cross-K/V
+    uint8_t* self_maps_dev = nullptr;         // [max_sessions] CUtensorMap over each session's self-K/V cache
     int n_align = 0;
 
     // encoder workspace (max_batch streams)
@@ -692,7 +693,12 @@ void decode_batch(wlk_engine* e, const int32_t* sids, int n, const int32_t* toke
             g.epi.layer = li; g.epi.n_head = H; g.epi.d_model = dt; g.epi.kv_len = ctx;
             run_gemm(e, g, WLK_KC_GEMM_DEC); }
         {   ProfScope ps(e, WLK_KC_ATTN_DEC_SELF);
-            dec_self_attention(e->dq, e->act, dj_dev, n, li, H, dt, ctx, e->datt, max_tq, e->st); }
+            // prefills on the tensor cores (causal, per-session cache planes through TMA); token steps and the fp32
+            // modes on the SIMT kernel
+            if (e->attn_backend == WLK_BACKEND_TCGEN05 && e->act == DT_BF16 && max_tq >= 16)
+                dec_self_attention_tcgen05(e->dq, R, dj_dev, n, max_tq, li, H, dt, ctx, e->self_maps_dev, e->datt, e->st);
+            else
+                dec_self_attention(e->dq, e->act, dj_dev, n, li, H, dt, ctx, e->datt, max_tq, e->st); }
         {   GemmArgs g;
             g.A = e->datt; g.a_type = e->act; g.lda = dt; g.W = L.Wo; g.w_type = e->wt; g.ldw = dt;
             g.M = R; g.N = dt; g.K = dt;
@@ -840,6 +846,11 @@ void alloc_session(wlk_engine* e, Session& s) {
         make_cross_kv_tmap(tmap, s.cross_kv, D.n_text_layer, D.n_text_head);
         const size_t slot = (size_t)(&s - e->sess.data());
         CUDA_CHECK(cudaMemcpy(e->kv_maps_dev + slot * 128, tmap, 128, cudaMemcpyHostToDevice));
+        make_self_kv_tmap(tmap, s.self_kv, D.n_text_layer, D.n_text_head, D.n_text_ctx);
+        CUDA_CHECK(cudaMemcpy(e->self_maps_dev + slot * 128, tmap, 128, cudaMemcpyHostToDevice));
+        // the tensor-core prefill reads whole 128-key tiles of the cache: rows past the current length take part in the
+        // MMAs with probability exactly 0, so they must hold finite values (0 x NaN would poison the accumulator)
+        CUDA_CHECK(cudaMemsetAsync(s.self_kv, 0, (size_t)D.n_text_layer * 2 * D.n_text_ctx * D.n_text_state * es, e->st));
     }
 }
 void free_session(wlk_engine* e, Session& s) {
@@ -875,6 +886,9 @@ void alloc_fork(wlk_engine* e, Session& s, int parent) {
         make_cross_kv_tmap(tmap, p.cross_kv, D.n_text_layer, D.n_text_head);
         const size_t slot = (size_t)(&s - e->sess.data());
         CUDA_CHECK(cudaMemcpy(e->kv_maps_dev + slot * 128, tmap, 128, cudaMemcpyHostToDevice));
+        make_self_kv_tmap(tmap, s.self_kv, D.n_text_layer, D.n_text_head, D.n_text_ctx);
+        CUDA_CHECK(cudaMemcpy(e->self_maps_dev + slot * 128, tmap, 128, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemsetAsync(s.self_kv, 0, (size_t)D.n_text_layer * 2 * D.n_text_ctx * D.n_text_state * es, e->st));
     }
 }
 
@@ -991,6 +1005,7 @@ void create_engine(const wlk_dims* dims, const wlk_config* cfg, wlk_engine** out
     CUDA_CHECK(cudaMallocHost(&e->res_host, sizeof(StepResult) * B));
     e->sess.resize(cfg->max_sessions);
     e->kv_maps_dev = reinterpret_cast<uint8_t*>(dmalloc_bytes((size_t)cfg->max_sessions * 128, acct));
+    e->self_maps_dev = reinterpret_cast<uint8_t*>(dmalloc_bytes((size_t)cfg->max_sessions * 128, acct));
     e->align_rank_host.assign((size_t)D.n_text_layer * D.n_text_head, -1);
     e->align_rank_dev = dmalloc<int32_t>(e, e->align_rank_host.size(), acct);
     CUDA_CHECK(cudaMemcpy(e->align_rank_dev, e->align_rank_host.data(), e->align_rank_host.size() * 4, cudaMemcpyHostToDevice));
@@ -1003,7 +1018,7 @@ void destroy_engine(wlk_engine* e) {
     for (auto& s : e->sess) if (s.open) free_session(e, s);
     void* ptrs[] = {e->arena.base, e->stage_f32, e->mel_t, e->h1, e->x, e->xn, e->qkv, e->att, e->hid, e->audio_scratch, e->mel_scratch, e->beam_scratch, e->sk_scratch, e->sk_counters, e->a_split,
                     e->pad_rows_dev, e->xptrs_dev, e->dx, e->dxn, e->dq, e->datt, e->dhid, e->dsel, e->stg_dev,
-                    e->res_dev, e->align_rank_dev, e->kv_maps_dev, e->all_logits_dev};
+                    e->res_dev, e->align_rank_dev, e->kv_maps_dev, e->self_maps_dev, e->all_logits_dev};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->stg_host) cudaFreeHost(e->stg_host);
     if (e->res_host) cudaFreeHost(e->res_host);

@@ -87,6 +87,10 @@ void dec_cross_attention_tcgen05(const void* q, int total_rows, const DecJob* jo
                                  int n_head, int d_model, const void* kv_maps_dev, const int32_t* align_rank, void* out,
                                  cudaStream_t st);
 void make_cross_kv_tmap(void* tmap_out_host /* 128 bytes */, const void* cross_kv, int n_layer, int n_head);
+// tensor-core causal prefill of the decoder self-attention (bf16)
+void dec_self_attention_tcgen05(const void* q, int total_rows, const DecJob* jobs, int n_jobs, int max_rows, int layer,
+                                int n_head, int d_model, int n_text_ctx, const void* kv_maps_dev, void* out, cudaStream_t st);
+void make_self_kv_tmap(void* tmap_out_host /* 128 bytes */, const void* self_kv, int n_layer, int n_head, int n_text_ctx);
 
 struct LogitJob {               // one per session (device array)
     float* logits_last;
