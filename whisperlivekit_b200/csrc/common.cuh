@@ -86,7 +86,7 @@ inline size_t dtype_size(int t) { return t == DT_BF16 ? 2 : 4; }
 
 // ---------------------------------------------------------------------------------
 // GEMM epilogue description shared by the SIMT and the tcgen05 GEMM kernels.
-//   v = acc + bias[n];  if gelu: v = gelu_erf(v);  if n < scale_cols: v *= col_scale;
+//   v = acc + bias[n];  v = act(v) (gelu: 1 erf-GELU, 2 ReLU, 3 SiLU);  if n < scale_cols: v *= col_scale;
 //   if residual: v += residual[m, n];   then stored according to `mode`.
 // ---------------------------------------------------------------------------------
 enum EpiMode {
@@ -98,7 +98,7 @@ enum EpiMode {
 
 struct Epilogue {
     const float* bias = nullptr;     // [N] fp32 or null
-    int gelu = 0;
+    int gelu = 0;                    // activation: 0 none, 1 erf-GELU, 2 ReLU, 3 SiLU (x * sigmoid x)
     float col_scale = 1.f;
     int scale_cols = 0;              // columns [0, scale_cols) are multiplied by col_scale ...
     int scale_period = 0;            // ... taken modulo scale_period when it is non-zero
@@ -168,7 +168,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Apply the arithmetic part of the epilogue to one accumulator element.
 __device__ __forceinline__ float epi_math(const Epilogue& e, float v, int m, int n) {
     if (e.bias) v += __ldg(e.bias + n);
-    if (e.gelu) v = gelu_erf(v);
+    if (e.gelu == 1) v = gelu_erf(v);
+    else if (e.gelu == 2) v = fmaxf(v, 0.f);
+    else if (e.gelu == 3) v = v / (1.0f + expf(-v));
     if ((e.scale_period ? (n % e.scale_period) : n) < e.scale_cols) v *= e.col_scale;
     if (e.residual) {
         int rr = (e.mode == EPI_ROWPTR) ? (m % e.rows_per_batch) : m;

@@ -83,9 +83,15 @@ __device__ __forceinline__ void epilogue_warp_tile(const Epilogue& epi, float* s
                 v[4 * j4] += b.x; v[4 * j4 + 1] += b.y; v[4 * j4 + 2] += b.z; v[4 * j4 + 3] += b.w;
             }
         }
-        if (epi.gelu) {
+        if (epi.gelu == 1) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = gelu_erf_fast(v[j]);
+        } else if (epi.gelu == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (epi.gelu == 3) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
         }
         if ((epi.scale_period ? (n0 % epi.scale_period) : n0) < epi.scale_cols) {
 #pragma unroll
