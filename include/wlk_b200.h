@@ -267,6 +267,53 @@ int wlk_vad_session_close(wlk_vad* v, int32_t sid);
 int wlk_vad_forward(wlk_vad* v, const int32_t* sids, int n, const float* pcm_host, const int32_t* window_offsets,
                     float* probs_host);
 
+/* =====================================================================================
+ * Streaming Sortformer diarizer forward (seam 8b-3).  Replaces what
+ * SortformerDiarizationOnline.diarize() runs per 1.0 s chunk and stream (reference whisperlivekit/diarization/
+ * sortformer_backend.py:253-311): AudioToMelSpectrogramPreprocessor.get_features (:181-188, :273), the 99-frame overlap
+ * with the previous chunk (:277-283) and NeMo's SortformerEncLabelModel.forward_streaming_step (:293-300) with the
+ * streaming parameters of :120-126 and the per-stream state of :212-234 (speaker cache, FIFO, silence profile).  The
+ * arithmetic is NeMo's (absent from the reference tree); it is restated in oracle/sortformer_oracle.py, PARITY UNPINNED.
+ * Tensor names are the NeMo state_dict keys ("encoder.pre_encode.conv.0.weight", "encoder.layers.N.self_attn.linear_q.
+ * weight", "transformer_encoder.layers.N.first_sub_layer.query_net.weight", "sortformer_modules.encoder_proj.weight", ...)
+ * plus "mel_filters" [n_mels][n_fft/2+1].  Sessions hold the state the reference keeps in StreamingSortformerState +
+ * _previous_chunk_features + total_preds; many streams are served by one call.
+ * ===================================================================================== */
+typedef struct wlk_sf wlk_sf;
+typedef struct wlk_sf_dims {
+    int32_t n_mels, n_fft, win_length, hop;                 /* front end: 128, 512, 400, 160                            */
+    int32_t conv_channels, d_model, n_head, n_layer, ff_mult, conv_kernel;   /* FastConformer: 256, 512, 8, 17, 4, 9    */
+    int32_t tf_d_model, tf_n_head, tf_n_layer, tf_inner, n_spk;              /* Transformer + head: 192, 8, 18, 768, 4  */
+    int32_t spkcache_len, fifo_len, spkcache_update_period, chunk_len, subsampling_factor;   /* :120-126                */
+    int32_t encoder_subsampling, spkcache_sil_frames_per_spk;                /* 8, 3                                    */
+    float pred_score_threshold, scores_boost_latest, sil_threshold;          /* SortformerModules defaults 0.25, 0.05,  */
+    float strong_boost_rate, weak_boost_rate, min_pos_scores_rate;           /* 0.2, 0.75, 1.5, 0.5                     */
+} wlk_sf_dims;
+int wlk_sf_create(const wlk_sf_dims* dims, const wlk_config* cfg, wlk_sf** out);    /* SortformerDiarization._load_model :68-128 */
+int wlk_sf_destroy(wlk_sf* q);
+int wlk_sf_load_tensor(wlk_sf* q, const char* name, const float* host, const int64_t* shape, int ndim);
+int wlk_sf_finalize_weights(wlk_sf* q);
+int wlk_sf_session_open(wlk_sf* q, int32_t* sid);          /* SortformerDiarizationOnline.__init__ / _init_streaming_state :151-234 */
+int wlk_sf_session_close(wlk_sf* q, int32_t sid);
+int wlk_sf_session_reset(wlk_sf* q, int32_t sid);
+/* diarize() (:253-311) for n streams: stream i hands in exactly chunk_len * subsampling_factor * hop samples
+ * (pcm_host[sample_offsets[i] .. sample_offsets[i+1])); chunk_preds of stream i -- the rows forward_streaming_step
+ * appends to total_preds -- land in chunk_preds_host[row_offsets_out[i] .. row_offsets_out[i+1]) x n_spk (may be NULL:
+ * the rows also stay on the device, see wlk_sf_total_preds).  row_offsets_out has n + 1 entries.                       */
+int wlk_sf_step_audio(wlk_sf* q, const int32_t* sids, int n, const float* pcm_host, const int64_t* sample_offsets,
+                      float* chunk_preds_host, int32_t* row_offsets_out);
+/* forward_streaming_step (:293-300) itself: time-major features [frames][n_mels] per stream (frame_offsets, n + 1
+ * entries), left_offset / right_offset in feature frames as the reference passes them.                                 */
+int wlk_sf_step_features(wlk_sf* q, const int32_t* sids, int n, const float* feats_host, const int32_t* frame_offsets,
+                         int32_t left_offset, int32_t right_offset, float* chunk_preds_host, int32_t* row_offsets_out);
+/* device-resident total_preds [n_rows][n_spk] of a stream (the tail the reference keeps, :301-305): feed it to
+ * wlk_diar_segments so only segments cross PCIe.                                                                       */
+int wlk_sf_total_preds(wlk_sf* q, int32_t sid, const float** preds_dev, int32_t* n_rows);
+/* parity taps: lengths[4] = spkcache rows, fifo rows, n_sil_frames, chunk index; buffers may be NULL                   */
+int wlk_sf_read_state(wlk_sf* q, int32_t sid, int32_t* lengths, float* spkcache_host, float* spkcache_preds_host,
+                      float* fifo_host, float* mean_sil_host);
+int wlk_sf_memory(wlk_sf* q, size_t* weights, size_t* sessions, size_t* workspace);
+
 #ifdef __cplusplus
 }
 #endif

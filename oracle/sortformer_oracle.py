@@ -49,6 +49,16 @@ def log_mel(audio: np.ndarray, d: SortformerDims) -> torch.Tensor:
     return torch.log(fb @ power + LOG_GUARD)
 
 
+def _topk_indices(x: torch.Tensor, k: int) -> torch.Tensor:
+    """Indices of the k largest entries of every column of x [n, c] -> [k, c].  NeMo calls torch.topk(sorted=False), whose
+    choice among EQUAL values is implementation-defined (and differs between torch's CPU and CUDA kernels); equal scores do
+    occur -- a frame kept for two overlapping speakers sits in the cache twice with identical predictions -- and the order
+    of the cache feeds the next step's relative-position attention.  Both this oracle and the CUDA kernel fix the choice:
+    among equal values the lower index wins (a stable descending sort)."""
+    order = torch.sort(x, dim=0, descending=True, stable=True).indices
+    return order[:k]
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # model
 # ---------------------------------------------------------------------------------------------------------------
@@ -186,7 +196,7 @@ class SortformerOracle:
         k = min(n_boost, n)
         if k <= 0:
             return scores
-        _, idx = torch.topk(scores, k, dim=0, largest=True, sorted=False)
+        idx = _topk_indices(scores, k)
         scores = scores.clone()
         cols = torch.arange(scores.shape[1])[None, :].expand_as(idx)
         scores[idx, cols] -= scale * math.log(0.5)
@@ -213,7 +223,8 @@ class SortformerOracle:
         n_frames = scores.shape[0]
         n_no_sil = n_frames - d.spkcache_sil_frames_per_spk
         flat = scores.t().reshape(-1)                                                  # speaker-major
-        vals, idx = torch.topk(flat, d.spkcache_len, sorted=False)
+        idx = _topk_indices(flat[:, None], d.spkcache_len)[:, 0]
+        vals = flat[idx]
         idx = torch.where(vals != float("-inf"), idx, torch.tensor(d.max_index))
         idx, _ = torch.sort(idx)
         disabled = idx == d.max_index
@@ -239,7 +250,7 @@ class SortformerOracle:
     def init_state(self) -> dict:
         d = self.d
         return dict(spkcache=torch.zeros(d.spkcache_len, d.d_model), spkcache_preds=torch.zeros(d.spkcache_len, d.n_spk),
-                    spkcache_len=0, spkcache_preds_valid=False, fifo=torch.zeros(d.fifo_len, d.d_model),
+                    spkcache_len=0, fifo=torch.zeros(d.fifo_len, d.d_model),
                     fifo_preds=torch.zeros(d.fifo_len, d.n_spk), fifo_len=0, mean_sil_emb=torch.zeros(d.d_model), n_sil=0)
 
     def streaming_update(self, st: dict, chunk: torch.Tensor, preds: torch.Tensor, lc: int, rc: int) -> torch.Tensor:
@@ -273,13 +284,9 @@ class SortformerOracle:
             pop_emb, pop_preds = up_fifo[:pop], up_fifo_preds[:pop]
             st["mean_sil_emb"], st["n_sil"] = self.silence_profile(st["mean_sil_emb"], st["n_sil"], pop_emb, pop_preds)
             up_cache[sl:sl + pop] = pop_emb
-            if st["spkcache_preds_valid"]:
-                up_cache_preds[sl:sl + pop] = pop_preds
-            elif sl + pop > d.spkcache_len:
-                # first overflow: the cache rows get the predictions of this very step
-                up_cache_preds[:sl] = preds[:sl]
-                up_cache_preds[sl:sl + pop] = pop_preds
-                st["spkcache_preds_valid"] = True
+            # the reference allocates spkcache_preds up front (sortformer_backend.py:219-222), so NeMo's "cache predictions
+            # already exist" branch is the one taken from the first pop-out on: the popped rows keep this step's predictions
+            up_cache_preds[sl:sl + pop] = pop_preds
             sl += pop
             new_fl -= pop
             up_fifo[:new_fl] = up_fifo[pop:pop + new_fl].clone()

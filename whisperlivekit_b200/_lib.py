@@ -24,6 +24,15 @@ class wlk_qwen_dims(C.Structure):
         "chunk_frames", "block_frames", "left_context_steps", "block_bidirectional", "conv_out_bias")]
 
 
+class wlk_sf_dims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_mels", "n_fft", "win_length", "hop", "conv_channels", "d_model", "n_head", "n_layer", "ff_mult", "conv_kernel",
+        "tf_d_model", "tf_n_head", "tf_n_layer", "tf_inner", "n_spk", "spkcache_len", "fifo_len", "spkcache_update_period",
+        "chunk_len", "subsampling_factor", "encoder_subsampling", "spkcache_sil_frames_per_spk")] + [(n, C.c_float) for n in (
+        "pred_score_threshold", "scores_boost_latest", "sil_threshold", "strong_boost_rate", "weak_boost_rate",
+        "min_pos_scores_rate")]
+
+
 class wlk_config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "device", "precision", "max_sessions", "max_batch", "gemm_backend", "attn_backend",
@@ -81,6 +90,18 @@ SIGNATURES = {
     "wlk_vad_session_reset": (C.c_int, [_vp, C.c_int32]),
     "wlk_vad_session_close": (C.c_int, [_vp, C.c_int32]),
     "wlk_vad_forward": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "wlk_sf_create": (C.c_int, [_vp, _vp, _vp]),
+    "wlk_sf_destroy": (C.c_int, [_vp]),
+    "wlk_sf_load_tensor": (C.c_int, [_vp, C.c_char_p, _vp, _vp, C.c_int]),
+    "wlk_sf_finalize_weights": (C.c_int, [_vp]),
+    "wlk_sf_session_open": (C.c_int, [_vp, _vp]),
+    "wlk_sf_session_close": (C.c_int, [_vp, C.c_int32]),
+    "wlk_sf_session_reset": (C.c_int, [_vp, C.c_int32]),
+    "wlk_sf_step_audio": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "wlk_sf_step_features": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp]),
+    "wlk_sf_total_preds": (C.c_int, [_vp, C.c_int32, _vp, _vp]),
+    "wlk_sf_read_state": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
+    "wlk_sf_memory": (C.c_int, [_vp, _vp, _vp, _vp]),
     "wlk_diar_segments": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int]),
     "wlk_session_append_pcm16": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64]),
     "wlk_session_fork": (C.c_int, [_vp, C.c_int32, _vp]),
