@@ -20,7 +20,7 @@ Numbers in the one JSON line:
               and the backlog does not grow.  Host->device chunk copies and device->host results are inside.
   roofline    encoder GEMM class: algorithmic FLOPs / CUDA-event time inside the timed run vs the measured peak.
   exact_mode  the same scripted tick in WLK_PREC_BF16X3 (1e-3-on-logits mode): the price of exactness.
-  other_configs  BASELINE configs 2, 3, 5 in brief (each also runnable as the main line with --config).
+  other_configs  BASELINE configs 2, 3, 4 (per-GPU share: 64 streams + Sortformer), 5 in brief (each also the main line with --config).
   cpu_baseline / --impl reference: the STAGED UNMODIFIED reference (oracle/_ref: vendored torch Whisper behind its own
               AlignAtt hooks) on the host cores, same per-chunk workload (oracle/ref_driver.py).
 
@@ -49,7 +49,8 @@ WINDOW = 480000
 PREFIX = int(os.environ.get("WLK_BENCH_PREFIX", "48"))            # the headline workload: 48 + 8 (overrides are for experiments)
 STEPS_PER_CHUNK = int(os.environ.get("WLK_BENCH_STEPS", "8"))
 UNIT = "concurrent real-time streams (audio-s per wall-s)"
-CONFIGS = ["alignatt-large-v3", "alignatt-base-en-1stream", "localagreement-large-v3-64", "qwen-tower-128"]
+CONFIGS = ["alignatt-large-v3", "alignatt-base-en-1stream", "localagreement-large-v3-64", "alignatt-large-v3-sortformer-64",
+           "qwen-tower-128"]
 
 
 def load_peaks():
@@ -466,6 +467,81 @@ def config_localagreement_64(device=0, streams=64, ticks=3, eng=None):
                 metric=UNIT, value=streams * 1.0 / sec, ms_per_tick=sec * 1e3, rtf_per_stream=sec / 1.0, streams=streams)
 
 
+def config_alignatt_sortformer(device=0, streams=64, seconds=4, eng=None):
+    """Config 4 per GPU: whisper large-v3 AlignAtt ticks at 0.5 s chunks PLUS the streaming Sortformer at its native 1.0 s
+    step (two Whisper ticks per diarization step), `streams` streams on one GPU (512 streams = 64 per GPU x 8).
+    Host chunks in for both engines, tokens / speaker segments out.  Weights: seeded, true geometries (no checkpoint in
+    either container; the Sortformer oracle is parity-unpinned, see oracle/sortformer_oracle.py)."""
+    import torch
+    from whisperlivekit_b200.dims import ALIGNMENT_HEADS, DIMS
+    from whisperlivekit_b200.engine import WhisperEngine
+    from whisperlivekit_b200.sortformer_dims import SORTFORMER_DIMS, synthetic_sortformer_state_dict, synthetic_two_speaker_audio
+    from whisperlivekit_b200.sortformer_engine import B200SortformerDiarization, B200SortformerDiarizationOnline, diarize_batch
+    from whisperlivekit_b200.weights import synthetic_audio, synthetic_state_dict
+    dims = DIMS["large-v3"]
+    own = eng is None
+    if own:
+        eng = WhisperEngine(dims, synthetic_state_dict(dims, seed=0), ALIGNMENT_HEADS["large-v3"], precision="bf16", device=device,
+                            max_sessions=streams, max_batch=streams)
+    sd = SORTFORMER_DIMS["diar_streaming_sortformer_4spk-v2"]
+    shared = B200SortformerDiarization(sd, synthetic_sortformer_state_dict(sd, 0), precision="bf16", device=device,
+                                       max_sessions=streams, max_batch=streams)
+    ons = [B200SortformerDiarizationOnline(shared) for _ in range(streams)]
+    rng = np.random.default_rng(5)
+    base = synthetic_audio(36.0, seed=7)
+    two = synthetic_two_speaker_audio(seconds + 14.0, seed=3)
+    sids = [eng.open_session() for _ in range(streams)]
+    for s in sids:
+        off = int(rng.integers(0, 16000 * 5))
+        eng.append_audio(s, base[off: off + WINDOW])
+    sp = eng.specials
+    prefix = list(sp.sot_sequence_including_notimestamps()) + list(range(1000, 1000 + PREFIX - 4))
+    sup = sp.alignatt_suppress_tokens()
+
+    def whisper_tick(k):
+        for i, s in enumerate(sids):
+            eng.drop_audio(s, CHUNK)
+            eng.append_audio(s, two[(k * CHUNK + 131 * i) % 100000: (k * CHUNK + 131 * i) % 100000 + CHUNK])
+        eng.encode(sids)
+        eng.decode(sids, [prefix] * streams)
+        eng.no_speech_prob(sids)
+        for _ in range(STEPS_PER_CHUNK):
+            r = eng.select(sids, sup)
+            eng.decode(sids, [[t[0]] for t in r])
+
+    def second(k):
+        whisper_tick(2 * k)
+        segs = diarize_batch(ons, [np.roll(two[k * 16000:(k + 1) * 16000], 37 * i) for i in range(streams)])
+        whisper_tick(2 * k + 1)
+        eng.sync()
+        return segs
+
+    for k in range(10):                                   # fill the speaker caches (188 + 188 rows) before timing
+        diarize_batch(ons, [np.roll(two[k * 16000:(k + 1) * 16000], 37 * i) for i in range(streams)])
+    second(10)
+    per, diar = [], []
+    for k in range(seconds):
+        t0 = time.perf_counter()
+        second(11 + k)
+        per.append(time.perf_counter() - t0)
+    for k in range(3):                                    # the diarization leg alone, same state
+        t0 = time.perf_counter()
+        diarize_batch(ons, [np.roll(two[k * 16000:(k + 1) * 16000], 37 * i) for i in range(streams)])
+        diar.append(time.perf_counter() - t0)
+    for o in ons:
+        o.close()
+    shared.close()
+    for s in sids:
+        eng.close_session(s)
+    if own:
+        eng.close()
+    sec = float(np.mean(per))
+    return dict(workload=f"whisper large-v3 AlignAtt (0.5 s chunks, {PREFIX}+{STEPS_PER_CHUNK} tokens per chunk, full 30 s re-encode) + streaming "
+                         f"Sortformer 4spk-v2 geometry (1.0 s steps, caches full: 401 rows per stream), {streams} streams per GPU, host chunks in",
+                metric=UNIT, value=streams * 1.0 / sec, ms_per_audio_second=sec * 1e3, rtf_per_stream=sec,
+                sortformer_ms_per_step=float(np.mean(diar) * 1e3), streams=streams)
+
+
 def config_qwen_tower(device=0, streams=128, ticks=24):
     """Config 5: Qwen3-ASR-0.6B causal audio tower, 0.25 s chunks (raw audio in, device log-mel), encoder fires per
     192-frame block, `streams` streams with staggered block phases."""
@@ -504,7 +580,7 @@ def config_qwen_tower(device=0, streams=128, ticks=24):
 
 def run_side_config(name, device):
     fn = {"alignatt-base-en-1stream": config_base_en_single_stream, "localagreement-large-v3-64": config_localagreement_64,
-          "qwen-tower-128": config_qwen_tower}[name]
+          "alignatt-large-v3-sortformer-64": config_alignatt_sortformer, "qwen-tower-128": config_qwen_tower}[name]
     try:
         return fn(device)
     except Exception as e:                                                # noqa: BLE001
@@ -555,13 +631,25 @@ def main():
     if args.config != "alignatt-large-v3":
         import torch
         torch.cuda.set_device(local_rank)
-        if rank != 0:
+        sharded = args.config == "alignatt-large-v3-sortformer-64" and world > 1      # config 4: every rank carries 64 streams
+        if rank != 0 and not sharded:
             return
+        if sharded:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         sampler = ClockSampler(local_rank); sampler.start()
         r = run_side_config(args.config, local_rank)
         clocks = sampler.summary()
+        if sharded:
+            t = torch.tensor([r.get("rtf_per_stream", 1e9)], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)                                 # the slowest rank sets the rate
+            r["rtf_per_stream"] = float(t.item())
+            r["value"] = r["streams"] * world / r["rtf_per_stream"]
+            dist.barrier(); dist.destroy_process_group()
+            if rank != 0:
+                return
         hib = args.config != "alignatt-base-en-1stream"
-        print(json.dumps(dict(metric=r.get("metric"), value=r.get("value", r.get("ms_p50")), unit=r.get("metric"), n_gpus=1,
+        print(json.dumps(dict(metric=r.get("metric"), value=r.get("value", r.get("ms_p50")), unit=r.get("metric"), n_gpus=world if sharded else 1,
                               steps=args.steps, warmup=args.warmup, higher_is_better=hib, scaling="weak", vs_baseline=None,
                               dtype="bf16", data="synthetic", config=dict(workload=r.get("workload"), name=args.config),
                               e2e=dict(value=r.get("value", r.get("ms_p50")), unit=r.get("metric"),
@@ -706,12 +794,16 @@ def main():
         b0 = args.seam_streams or max(16, (2 * B // 3) // 16 * 16)
         seam_best, seam_probes = seam_search(eng, b0, seam_bmax, world, rng, args.seam_ticks, 6, mode=args.seam_mode)
         note("seam probes: " + json.dumps(seam_probes))
-    la64 = None
+    la64, diar64 = None, None
     if not args.no_extras and args.precision == "bf16" and rank == 0 and world == 1 and max(B, seam_bmax) >= 64:
         try:
             la64 = config_localagreement_64(local_rank, eng=eng)
         except Exception as e:                                            # noqa: BLE001
             la64 = dict(error=repr(e))
+        try:
+            diar64 = config_alignatt_sortformer(local_rank, eng=eng)
+        except Exception as e:                                            # noqa: BLE001
+            diar64 = dict(error=repr(e))
     eng.close()
 
     exact, others = None, None
@@ -726,8 +818,8 @@ def main():
                      parity="|dlogits| 2.4e-4 vs the reference at large-v3, tokens and frames identical (tests/test_gpu_large_v3.py)",
                      value=Bx * world * CHUNK_S / (msx / 1e3), unit=UNIT, streams_per_gpu=Bx, ms_per_step=msx)
         if rank == 0 and world == 1:
-            others = {c: (la64 if c == "localagreement-large-v3-64" and la64 is not None else run_side_config(c, local_rank))
-                      for c in CONFIGS[1:]}
+            reuse = {"localagreement-large-v3-64": la64, "alignatt-large-v3-sortformer-64": diar64}
+            others = {c: (reuse[c] if reuse.get(c) is not None else run_side_config(c, local_rank)) for c in CONFIGS[1:]}
 
     if rank == 0:
         peaks = load_peaks()
