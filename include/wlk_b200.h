@@ -106,6 +106,19 @@ int wlk_sessions_gather_decoder(wlk_engine* e, const int32_t* sessions, const in
  *   inference epoch for the session (the reference drops its KV cache after every infer,
  *   align_att_base.py:312).  content_mel_len_out[i] as simul_whisper.py:350.              */
 int wlk_encode(wlk_engine* e, const int32_t* sids, int n, int32_t* content_mel_len_out);
+/* wlk_encode_incremental: the same hook in the LABELLED APPROXIMATE incremental mode (north_star item 2; SURVEY.md
+ *   section 7 H1): the K/V of every encoder layer are retained per session, and per call only a block of positions --
+ *   two left of the old content end, the appended frames, two of padding (plus the vacated tail after a slide of the
+ *   rolling window, simul_whisper.py:224-236) -- runs through the conv stem and the layers, attending to the retained
+ *   K/V of every other position.  The first call of a stream takes the whole window as its block and equals wlk_encode;
+ *   buffers are ring-addressed after a slide (nothing is moved).  Not bit- or 1e-3-comparable with the reference by
+ *   construction: graded by token / attended-frame agreement with the parity mode.  bf16 tcgen05 mode only.
+ *   block_rows_out[i] (may be NULL) = positions that went through the encoder for session i.                          */
+int wlk_encode_incremental(wlk_engine* e, const int32_t* sids, int n, int32_t* content_mel_len_out, int32_t* block_rows_out);
+/* forget the retained encoder K/V of a session: its next wlk_encode_incremental takes the whole window as its block
+ * (= the parity computation); a host calls this to bound the drift of the approximate mode (also: WLK_INC_REFRESH=k
+ * makes every k-th chunk such a block).                                                                              */
+int wlk_session_reset_incremental(wlk_engine* e, int32_t sid);
 /* wlk_decode: AlignAtt._get_logits_and_cross_attn (simul_whisper.py:357-368) =
  *   TextDecoder.forward with kv_cache + return_cross_attn (model.py:281-332).  Feeds
  *   tokens[offsets[i]..offsets[i+1]) to session i at its current self-KV offset.  Keeps

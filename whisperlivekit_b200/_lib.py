@@ -107,6 +107,8 @@ SIGNATURES = {
     "wlk_session_fork": (C.c_int, [_vp, C.c_int32, _vp]),
     "wlk_sessions_gather_decoder": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "wlk_encode": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "wlk_encode_incremental": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    "wlk_session_reset_incremental": (C.c_int, [_vp, C.c_int32]),
     "wlk_decode": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int32]),
     "wlk_encode_mel": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32]),
     "wlk_decode_all_logits": (C.c_int, [_vp, C.c_int32, _vp, C.c_int, C.c_int32, _vp]),

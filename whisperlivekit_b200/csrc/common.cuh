@@ -116,8 +116,8 @@ struct Epilogue {
     int n_head = 0, d_model = 0;         // head-major scatters
     int kv_len = 0;                      // rows per (layer,kv,head) plane: 1500 (cross) / n_text_ctx (self)
     int layer = 0;                       // EPI_SELF_QKV
-    const int32_t* row_slot = nullptr;   // EPI_SELF_QKV: row -> index into batch_ptrs
-    const int32_t* row_pos = nullptr;    // EPI_SELF_QKV: row -> position in the self-KV cache
+    const int32_t* row_slot = nullptr;   // EPI_SELF_QKV (and EPI_XKV when set): row -> index into batch_ptrs
+    const int32_t* row_pos = nullptr;    // EPI_SELF_QKV (and EPI_XKV when set): row -> row of the K/V plane
 };
 
 struct GemmArgs {
@@ -193,8 +193,9 @@ __device__ __forceinline__ int64_t epi_index(const Epilogue& e, int m, int n, vo
             return (int64_t)r * e.ldc + n;
         }
         case EPI_XKV: {
-            // n -> (layer, kv, head, e);  m -> (batch b, frame r)
+            // n -> (layer, kv, head, e);  m -> (batch b, frame r), or through the row maps when they are given
             int b = m / e.rows_per_batch, r = m - b * e.rows_per_batch;
+            if (e.row_slot) { b = e.row_slot[m]; r = e.row_pos[m]; }
             int two_d = 2 * e.d_model;
             int l = n / two_d, rem = n - l * two_d;
             int kv = rem / e.d_model, c = rem - kv * e.d_model;
@@ -297,6 +298,7 @@ __device__ __forceinline__ EpiRow epi_row(const Epilogue& e, int m, int M) {
         }
         case EPI_XKV: {
             int b = m / e.rows_per_batch, rr = m - b * e.rows_per_batch;
+            if (e.row_slot) { b = e.row_slot[m]; rr = e.row_pos[m]; }     // incremental encoder: row -> (session, ring slot)
             r.ptr0 = reinterpret_cast<char*>(e.batch_ptrs[b]) + (int64_t)rr * 64 * es;
             break;
         }

@@ -75,6 +75,14 @@ struct Session {
     size_t bytes = 0;
     int parent = -1;      // >= 0: a beam fork -- audio/mel are null, xa / cross_kv alias the parent's buffers
     int n_forks = 0;      // open forks reading this session's encoder output
+    // incremental encoder (labelled approximate mode, encode_incremental): encoder K/V of every layer retained across
+    // chunks [L_enc][2][H][1500][64], ring-addressed: logical position p of the window lives in slot (p + rot) % 1500
+    void* enc_kv = nullptr;
+    bool inc_valid = false;
+    int rot = 0;
+    int inc_content = 0;          // positions of content covered by the last incremental encode
+    int64_t inc_dropped = 0;      // samples dropped at the front since then
+    int inc_chunks = 0;           // incremental encodes since the last full-window block
 };
 
 struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; };
@@ -114,6 +122,10 @@ struct wlk_engine {
     int32_t* align_rank_dev = nullptr;
     uint8_t* kv_maps_dev = nullptr;           // [max_sessions] CUtensorMap (128 B each) over each session's cross-K/V
     uint8_t* self_maps_dev = nullptr;         // [max_sessions] CUtensorMap over each session's self-K/V cache
+    uint8_t* enc_maps_dev = nullptr;          // [max_sessions] CUtensorMap over each session's retained encoder K/V
+    int32_t* enc_norank_dev = nullptr;        // [L_enc * H_enc] all -1: no head of the encoder is an alignment head
+    int32_t *inc_row_slot = nullptr, *inc_row_pos = nullptr;   // [max_batch * 1500] row maps of an incremental block
+    int inc_refresh = 0;                      // WLK_INC_REFRESH: a full-window block every this many chunks (0: never)
     int n_align = 0;
 
     // encoder workspace (max_batch streams)
@@ -473,6 +485,45 @@ Session& get_root_session(wlk_engine* e, int32_t sid, const char* what) {
 // ---------------------------------------------------------------------------------------
 void run_encoder(wlk_engine* e, const int32_t* sids, int n, void** xkv_dev);
 
+// One session's log-mel job (shared by the parity and the incremental encode): fills `mj`, moves the reusable raw rows of
+// the incremental log-mel, sets s.content_len.
+void fill_mel_job(wlk_engine* e, Session& s, MelJob& mj, int i, int& max_frames) {
+    const int nm = e->dims.n_mels;
+    const size_t es = e->es();
+    const int64_t N = s.audio_len;
+    const int64_t n_total = (N + 480000) / HOP;                 // torch.stft frames minus the dropped last one
+    int64_t n_compute = (N + 199) / HOP + 1;                   // frames whose window overlaps [0, N): all of them
+    if (n_compute > MEL_MAX_FRAMES) n_compute = MEL_MAX_FRAMES; // join the global max, also beyond the 30 s kept
+    if (n_compute > max_frames) max_frames = (int)n_compute;
+    mj.audio = s.audio; mj.raw = s.mel_raw; mj.blockmax = s.mel_blockmax;
+    mj.out = offs(e->mel_t, (size_t)i * MEL_ROWS * nm, es);
+    mj.n = (int32_t)N; mj.n_compute = (int32_t)n_compute; mj.n_total = (int32_t)n_total; mj.pad = 0;
+    mj.keep_lo = mj.keep_hi = 0;
+    // Incremental log-mel (exact).  Frame f of the window reads samples [160 f - 200, 160 f + 200).  After the window
+    // slid by d = mel_dropped / 160 whole frames and grew at the end, new frame f equals old frame f + d bit for bit
+    // as long as neither touches an edge: f >= 2 (no reflection at the new left edge; f + d >= 2 follows) and
+    // 160 f + 200 <= old end (the old pass saw the same samples, not the zero padding).  Those rows are moved, the
+    // two leading frames and the ~50 trailing ones are recomputed.
+    if (e->mel_incremental && s.mel_n >= 0 && s.mel_dropped % HOP == 0 && s.mel_dropped <= s.mel_n &&
+        n_compute <= MEL_STORE_FRAMES && (s.mel_n + 199) / HOP + 1 <= MEL_STORE_FRAMES) {
+        const int64_t d = s.mel_dropped / HOP;
+        const int64_t old_end = s.mel_n - s.mel_dropped;                   // old audio end in new coordinates
+        const int64_t lo = d == 0 ? 0 : 2;
+        int64_t hi = old_end >= 200 ? (old_end - 200) / HOP + 1 : 0;       // exclusive
+        if (hi > n_compute) hi = n_compute;
+        if (hi > lo) {
+            if (d > 0) {
+                const size_t bytes = (size_t)(hi - lo) * nm * 4;
+                CUDA_CHECK(cudaMemcpyAsync(e->mel_scratch, s.mel_raw + (size_t)(lo + d) * nm, bytes, cudaMemcpyDeviceToDevice, e->st));
+                CUDA_CHECK(cudaMemcpyAsync(s.mel_raw + (size_t)lo * nm, e->mel_scratch, bytes, cudaMemcpyDeviceToDevice, e->st));
+            }
+            mj.keep_lo = (int32_t)lo; mj.keep_hi = (int32_t)hi;
+        }
+    }
+    s.mel_n = N; s.mel_dropped = 0;
+    s.content_len = (int)((n_total - N_FRAMES) / 2);            // simul_whisper.py:350 (unclamped: the policy's
+}                                                               // frame_threshold test needs the true value)
+
 void encode_batch(wlk_engine* e, const int32_t* sids, int n, int32_t* content_out) {
     const wlk_dims& D = e->dims;
     Weights& W = e->w;
@@ -491,39 +542,8 @@ void encode_batch(wlk_engine* e, const int32_t* sids, int n, int32_t* content_ou
     int max_frames = 1;
     for (int i = 0; i < n; ++i) {
         Session& s = e->sess[sids[i]];
-        const int64_t N = s.audio_len;
-        const int64_t n_total = (N + 480000) / HOP;                 // torch.stft frames minus the dropped last one
-        int64_t n_compute = (N + 199) / HOP + 1;                   // frames whose window overlaps [0, N): all of them
-        if (n_compute > MEL_MAX_FRAMES) n_compute = MEL_MAX_FRAMES; // join the global max, also beyond the 30 s kept
-        if (n_compute > max_frames) max_frames = (int)n_compute;
-        mj[i].audio = s.audio; mj[i].raw = s.mel_raw; mj[i].blockmax = s.mel_blockmax;
-        mj[i].out = offs(e->mel_t, (size_t)i * MEL_ROWS * nm, es);
-        mj[i].n = (int32_t)N; mj[i].n_compute = (int32_t)n_compute; mj[i].n_total = (int32_t)n_total; mj[i].pad = 0;
-        mj[i].keep_lo = mj[i].keep_hi = 0;
-        // Incremental log-mel (exact).  Frame f of the window reads samples [160 f - 200, 160 f + 200).  After the window
-        // slid by d = mel_dropped / 160 whole frames and grew at the end, new frame f equals old frame f + d bit for bit
-        // as long as neither touches an edge: f >= 2 (no reflection at the new left edge; f + d >= 2 follows) and
-        // 160 f + 200 <= old end (the old pass saw the same samples, not the zero padding).  Those rows are moved, the
-        // two leading frames and the ~50 trailing ones are recomputed.
-        if (e->mel_incremental && s.mel_n >= 0 && s.mel_dropped % HOP == 0 && s.mel_dropped <= s.mel_n &&
-            n_compute <= MEL_STORE_FRAMES && (s.mel_n + 199) / HOP + 1 <= MEL_STORE_FRAMES) {
-            const int64_t d = s.mel_dropped / HOP;
-            const int64_t old_end = s.mel_n - s.mel_dropped;                   // old audio end in new coordinates
-            const int64_t lo = d == 0 ? 0 : 2;
-            int64_t hi = old_end >= 200 ? (old_end - 200) / HOP + 1 : 0;       // exclusive
-            if (hi > n_compute) hi = n_compute;
-            if (hi > lo) {
-                if (d > 0) {
-                    const size_t bytes = (size_t)(hi - lo) * nm * 4;
-                    CUDA_CHECK(cudaMemcpyAsync(e->mel_scratch, s.mel_raw + (size_t)(lo + d) * nm, bytes, cudaMemcpyDeviceToDevice, e->st));
-                    CUDA_CHECK(cudaMemcpyAsync(s.mel_raw + (size_t)lo * nm, e->mel_scratch, bytes, cudaMemcpyDeviceToDevice, e->st));
-                }
-                mj[i].keep_lo = (int32_t)lo; mj[i].keep_hi = (int32_t)hi;
-            }
-        }
-        s.mel_n = N; s.mel_dropped = 0;
-        s.content_len = (int)((n_total - N_FRAMES) / 2);            // simul_whisper.py:350 (unclamped: the policy's
-        content_out[i] = s.content_len;                             // frame_threshold test needs the true value)
+        fill_mel_job(e, s, mj[i], i, max_frames);
+        content_out[i] = s.content_len;
         xkv[i] = s.cross_kv;
     }
     sg.upload();
@@ -622,7 +642,180 @@ void run_encoder(wlk_engine* e, const int32_t* sids, int n, void** xkv_dev) {
     for (int i = 0; i < n; ++i) {
         Session& s = e->sess[sids[i]];
         s.self_len = 0; s.align_rows = 0; s.iter_row_start.clear(); s.encoded = true;
+        s.inc_valid = false; s.rot = 0;                  // the parity encode writes every buffer in logical order
         if (s.n_forks)                                   // a new epoch for the beams of this stream as well
+            for (auto& f : e->sess)
+                if (f.open && f.parent == sids[i]) { f.self_len = 0; f.align_rows = 0; f.iter_row_start.clear(); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Incremental encoder -- LABELLED APPROXIMATE (north_star item 2: "KV retained across chunk extensions so only the
+// appended frames are re-encoded"; SURVEY.md section 7 H1 explains why this cannot equal the reference's full re-encode:
+// Whisper's encoder is bidirectional, so new audio changes every position's output from layer 1 on).
+//   * every encoder layer's K/V of a stream is retained ([L][2][H][1500][64], like the cross-K/V);
+//   * per chunk only a BLOCK of positions runs through the conv stem and the layers: the two positions left of the old
+//     content end (conv receptive field), the new content and two positions of padding behind it -- ~29 rows instead of
+//     1500; the block attends to all 1500 slots: the retained K/V of everything outside the block (frozen as computed when
+//     those positions were last in a block) and the block's own fresh K/V (written by the QKV GEMM's scatter epilogue first);
+//   * the first encode of a stream (and every `inc_refresh`-th, and whenever the bookkeeping does not fit) takes the whole
+//     window as its block: that IS the parity computation (same kernels as the decoder's cross-attention prefill);
+//   * when the window slides by whole positions the buffers are not moved: position p lives in ring slot (p + rot) % 1500,
+//     rot advances by the dropped positions, and the vacated slots -- now the logical tail -- join the block.  Attention is
+//     order-free over keys; the two consumers of frame ORDER (the median-7 / argmax of the alignment reduction) read
+//     through `rot`.  Positional embeddings are taken by slot: a frame keeps the embedding it was encoded with, frames
+//     stay cyclically ordered, the wrap point travels through the window (the approximation's second source of error).
+// Evaluated by token / attended-frame agreement against the parity mode (tests/test_gpu_incremental.py, bench.py).
+// ---------------------------------------------------------------------------------------
+void ensure_incremental(wlk_engine* e, Session& s, int sid) {
+    const wlk_dims& D = e->dims;
+    if (!e->enc_maps_dev) {
+        size_t* acct = &e->bytes_workspace;
+        e->enc_maps_dev = reinterpret_cast<uint8_t*>(dmalloc_bytes((size_t)e->cfg.max_sessions * 128, acct));
+        std::vector<int32_t> none((size_t)D.n_audio_layer * D.n_audio_head, -1);
+        e->enc_norank_dev = dmalloc<int32_t>(e, none.size(), acct);
+        CUDA_CHECK(cudaMemcpy(e->enc_norank_dev, none.data(), none.size() * 4, cudaMemcpyHostToDevice));
+        e->inc_row_slot = dmalloc<int32_t>(e, (size_t)e->cfg.max_batch * N_CTX, acct);
+        e->inc_row_pos = dmalloc<int32_t>(e, (size_t)e->cfg.max_batch * N_CTX, acct);
+        const char* v = getenv("WLK_INC_REFRESH");
+        e->inc_refresh = v ? atoi(v) : 0;
+    }
+    if (!s.enc_kv) {
+        const size_t bytes = (size_t)D.n_audio_layer * 2 * N_CTX * D.n_audio_state * e->es();
+        s.enc_kv = dmalloc_bytes(bytes, &s.bytes);
+        e->bytes_sessions += bytes;
+        CUDA_CHECK(cudaMemsetAsync(s.enc_kv, 0, bytes, e->st));
+        alignas(64) uint8_t tmap[128];
+        make_cross_kv_tmap(tmap, s.enc_kv, D.n_audio_layer, D.n_audio_head);
+        CUDA_CHECK(cudaMemcpy(e->enc_maps_dev + (size_t)sid * 128, tmap, 128, cudaMemcpyHostToDevice));
+        s.inc_valid = false;
+    }
+}
+
+void encode_incremental(wlk_engine* e, const int32_t* sids, int n, int32_t* content_out, int32_t* block_rows_out) {
+    const wlk_dims& D = e->dims;
+    Weights& W = e->w;
+    const int d = D.n_audio_state, dt = D.n_text_state, nm = D.n_mels, H = D.n_audio_head;
+    const size_t es = e->es();
+    WLK_CHECK(e->act == DT_BF16 && e->wt == DT_BF16 && e->attn_backend == WLK_BACKEND_TCGEN05 && e->gemm_backend == WLK_BACKEND_TCGEN05,
+              "the incremental encoder runs in the bf16 tcgen05 mode only");
+    WLK_CHECK(n >= 1 && n <= e->cfg.max_batch, "encode batch %d outside [1, %d]", n, e->cfg.max_batch);
+    for (int i = 0; i < n; ++i) {
+        Session& s = get_root_session(e, sids[i], "encode");
+        WLK_CHECK(s.audio_len > 0, "session %d has no audio", sids[i]);
+        for (int j = 0; j < i; ++j) WLK_CHECK(sids[j] != sids[i], "session %d appears twice in the batch", sids[i]);
+    }
+    for (int i = 0; i < n; ++i) ensure_incremental(e, e->sess[sids[i]], sids[i]);
+
+    Stager sg(e);
+    MelJob* mj_dev; MelJob* mj = sg.host<MelJob>(n, &mj_dev);
+    IncJob* ij_dev; IncJob* ij = sg.host<IncJob>(n, &ij_dev);
+    DecJob* dj_dev; DecJob* dj = sg.host<DecJob>(n, &dj_dev);
+    void** ekv_dev; void** ekv = sg.host<void*>(n, &ekv_dev);
+    void** xkv_dev; void** xkv = sg.host<void*>(n, &xkv_dev);
+    int max_frames = 1, R = 0, R1 = 0, max_rows = 0;
+    std::vector<int> new_rot(n), new_chunks(n);
+    for (int i = 0; i < n; ++i) {
+        Session& s = e->sess[sids[i]];
+        fill_mel_job(e, s, mj[i], i, max_frames);
+        content_out[i] = s.content_len;
+        const int C = std::min(s.content_len, N_CTX);
+        int p0 = 0, p1 = N_CTX, rot = 0, chunks = 0;
+        const bool whole = !s.inc_valid || s.inc_dropped % 320 != 0 || s.inc_dropped / 320 > s.inc_content ||
+                           (e->inc_refresh > 0 && s.inc_chunks + 1 >= e->inc_refresh);
+        if (!whole) {
+            const int dpos = (int)(s.inc_dropped / 320);
+            rot = (s.rot + dpos) % N_CTX;
+            const int old_end = s.inc_content - dpos;                      // old content end in the new coordinates
+            p0 = std::max(0, std::min(old_end, C) - 2);
+            p1 = dpos > 0 ? N_CTX : std::min(N_CTX, std::max(C, old_end) + 2);   // a slide hands the vacated tail slots to the block
+            chunks = s.inc_chunks + 1;
+        }
+        new_rot[i] = rot; new_chunks[i] = chunks;
+        const int len = p1 - p0;
+        ij[i].mel = mj[i].out; ij[i].xa = s.xa; ij[i].p0 = p0; ij[i].p1 = p1; ij[i].rot = rot;
+        ij[i].row1_off = R1; ij[i].row_off = R; ij[i].pad = 0;
+        memset(&dj[i], 0, sizeof(DecJob));
+        dj[i].row_off = R; dj[i].n_rows = len; dj[i].slot = sids[i];
+        ekv[i] = s.enc_kv; xkv[i] = s.cross_kv;
+        if (block_rows_out) block_rows_out[i] = len;
+        R += len; R1 += 2 * len + 1;
+        max_rows = std::max(max_rows, len);
+    }
+    sg.upload();
+    {   ProfScope ps(e, WLK_KC_MEL, 0, (double)n * (480000.0 * 4 + 3000.0 * nm * es));
+        mel_forward(mj_dev, n, nm, W.filtT, W.window, W.twiddle, W.filt_span, e->act, max_frames, e->st); }
+
+    // conv stem over the block: gathered operand rows, two ordinary GEMMs
+    void* A1 = e->h1; void* H1 = e->qkv; void* A2 = e->hid;
+    float* posbuf = reinterpret_cast<float*>(e->h1);                      // A1 is dead once conv1 has run
+    {   ProfScope ps(e, WLK_KC_MISC);
+        inc_gather_conv1(ij_dev, n, 2 * max_rows + 1, nm, A1, e->act, e->st); }
+    {   GemmArgs g;
+        g.A = A1; g.a_type = e->act; g.lda = 3 * nm; g.W = W.Wc1; g.w_type = e->wt; g.ldw = 3 * nm;
+        g.M = R1; g.N = d; g.K = 3 * nm;
+        g.epi.bias = W.bc1; g.epi.gelu = 1; g.epi.C = H1; g.epi.c_type = e->act; g.epi.ldc = d;
+        run_gemm(e, g, WLK_KC_GEMM_ENC); }
+    {   ProfScope ps(e, WLK_KC_MISC);
+        inc_gather_conv2(ij_dev, n, max_rows, d, H1, A2, W.enc_pos, posbuf, e->inc_row_slot, e->inc_row_pos, e->act, e->st); }
+    {   GemmArgs g;
+        g.A = A2; g.a_type = e->act; g.lda = 3 * d; g.W = W.Wc2; g.w_type = e->wt; g.ldw = 3 * d;
+        g.M = R; g.N = d; g.K = 3 * d;
+        g.epi.bias = W.bc2; g.epi.gelu = 1; g.epi.residual = posbuf; g.epi.ldr = d;
+        g.epi.C = e->x; g.epi.c_type = DT_F32; g.epi.ldc = d;
+        run_gemm(e, g, WLK_KC_GEMM_ENC); }
+
+    const float qk_scale = powf(64.0f, -0.25f);
+    for (int li = 0; li < D.n_audio_layer; ++li) {
+        EncLayerW& L = W.enc[li];
+        {   ProfScope ps(e, WLK_KC_LN, 0, (double)R * d * (4 + es));
+            layernorm(e->x, d, L.ln1w, L.ln1b, e->xn, e->act, d, R, d, nullptr, e->st); }
+        {   GemmArgs g;                                                   // q -> packed rows, k / v -> the ring slots
+            g.A = e->xn; g.a_type = e->act; g.lda = d; g.W = L.Wqkv; g.w_type = e->wt; g.ldw = d;
+            g.M = R; g.N = 3 * d; g.K = d;
+            g.epi.bias = L.bqkv; g.epi.col_scale = qk_scale; g.epi.scale_cols = 2 * d;
+            g.epi.mode = EPI_SELF_QKV; g.epi.C = e->qkv; g.epi.ldc = d; g.epi.c_type = e->act;
+            g.epi.batch_ptrs = ekv_dev; g.epi.row_slot = e->inc_row_slot; g.epi.row_pos = e->inc_row_pos;
+            g.epi.layer = li; g.epi.n_head = H; g.epi.d_model = d; g.epi.kv_len = N_CTX;
+            run_gemm(e, g, WLK_KC_GEMM_ENC); }
+        {   ProfScope ps(e, WLK_KC_ATTN_ENC, 4.0 * H * (double)R * N_CTX * 64, (double)n * 2 * d * N_CTX * es);
+            dec_cross_attention_tcgen05(e->qkv, R, dj_dev, n, max_rows, li, H, d, e->enc_maps_dev, e->enc_norank_dev, e->att, e->st); }
+        {   GemmArgs g;
+            g.A = e->att; g.a_type = e->act; g.lda = d; g.W = L.Wo; g.w_type = e->wt; g.ldw = d;
+            g.M = R; g.N = d; g.K = d;
+            g.epi.bias = L.bo; g.epi.residual = e->x; g.epi.ldr = d; g.epi.C = e->x; g.epi.c_type = DT_F32; g.epi.ldc = d;
+            run_gemm(e, g, WLK_KC_GEMM_ENC); }
+        {   ProfScope ps(e, WLK_KC_LN, 0, (double)R * d * (4 + es));
+            layernorm(e->x, d, L.ln2w, L.ln2b, e->xn, e->act, d, R, d, nullptr, e->st); }
+        {   GemmArgs g;
+            g.A = e->xn; g.a_type = e->act; g.lda = d; g.W = L.W1; g.w_type = e->wt; g.ldw = d;
+            g.M = R; g.N = 4 * d; g.K = d;
+            g.epi.bias = L.b1; g.epi.gelu = 1; g.epi.C = e->hid; g.epi.c_type = e->act; g.epi.ldc = 4 * d;
+            run_gemm(e, g, WLK_KC_GEMM_ENC); }
+        {   GemmArgs g;
+            g.A = e->hid; g.a_type = e->act; g.lda = 4 * d; g.W = L.W2; g.w_type = e->wt; g.ldw = 4 * d;
+            g.M = R; g.N = d; g.K = 4 * d;
+            g.epi.bias = L.b2; g.epi.residual = e->x; g.epi.ldr = d; g.epi.C = e->x; g.epi.c_type = DT_F32; g.epi.ldc = d;
+            run_gemm(e, g, WLK_KC_GEMM_ENC); }
+    }
+    {   ProfScope ps(e, WLK_KC_LN, 0, (double)R * d * (4 + es));
+        layernorm(e->x, d, W.lnpw, W.lnpb, e->xn, e->act, d, R, d, nullptr, e->st); }
+    {   ProfScope ps(e, WLK_KC_MISC);
+        inc_scatter_rows(ij_dev, n, max_rows, d, e->xn, e->act, e->st); }
+    {   GemmArgs g;                                                       // cross-K/V of the block's rows only
+        g.A = e->xn; g.a_type = e->act; g.lda = d; g.W = W.Wxkv; g.w_type = e->wt; g.ldw = d;
+        g.M = R; g.N = D.n_text_layer * 2 * dt; g.K = d;
+        g.epi.bias = W.bxkv; g.epi.col_scale = qk_scale; g.epi.scale_cols = dt; g.epi.scale_period = 2 * dt;
+        g.epi.mode = EPI_XKV; g.epi.batch_ptrs = xkv_dev; g.epi.rows_per_batch = N_CTX;
+        g.epi.row_slot = e->inc_row_slot; g.epi.row_pos = e->inc_row_pos;
+        g.epi.n_head = D.n_text_head; g.epi.d_model = dt; g.epi.kv_len = N_CTX; g.epi.c_type = e->act;
+        run_gemm(e, g, WLK_KC_GEMM_XKV); }
+    for (int i = 0; i < n; ++i) {
+        Session& s = e->sess[sids[i]];
+        s.self_len = 0; s.align_rows = 0; s.iter_row_start.clear(); s.encoded = true;
+        s.inc_valid = true; s.rot = new_rot[i]; s.inc_chunks = new_chunks[i];
+        s.inc_content = std::min(s.content_len, N_CTX); s.inc_dropped = 0;
+        if (s.n_forks)
             for (auto& f : e->sess)
                 if (f.open && f.parent == sids[i]) { f.self_len = 0; f.align_rows = 0; f.iter_row_start.clear(); }
     }
@@ -820,6 +1013,7 @@ LogitJob make_logit_job(wlk_engine* e, Session& s, int window_iters, int full) {
     // the reference slices a 1500-wide tensor ([:, :, :content_mel_len], simul_whisper.py:433): frames >= 1500 do not exist
     j.content_len = std::min(enc_owner(e, s).content_len, N_CTX);
     j.full = full;
+    j.rot = enc_owner(e, s).rot;
     return j;
 }
 
@@ -859,7 +1053,7 @@ void free_session(wlk_engine* e, Session& s) {
         s.xa = nullptr; s.cross_kv = nullptr;
     }
     void* ptrs[] = {s.audio, s.mel_raw, s.mel_blockmax, s.xa, s.cross_kv, s.self_kv, s.align, s.logits_last,
-                    s.logits_sot, s.attn_out, s.stats};
+                    s.logits_sot, s.attn_out, s.stats, s.enc_kv};
     for (void* p : ptrs) if (p) cudaFree(p);
     e->bytes_sessions -= s.bytes;
     s = Session{};
@@ -1267,6 +1461,7 @@ int wlk_session_drop_audio(wlk_engine* e, int32_t sid, int64_t n) {
         CUDA_CHECK(cudaMemcpyAsync(s.audio, e->audio_scratch, (size_t)keep * 4, cudaMemcpyDeviceToDevice, e->st));
     }
     if (s.mel_n >= 0) s.mel_dropped += n;
+    if (s.inc_valid) s.inc_dropped += n;
     s.audio_len = keep;
     WLK_API_END
 }
@@ -1274,7 +1469,7 @@ int wlk_session_clear_audio(wlk_engine* e, int32_t sid) {
     WLK_API_BEGIN
     LOCK(e);
     Session& s = get_session(e, sid);
-    s.audio_len = 0; s.mel_n = -1; s.mel_dropped = 0;
+    s.audio_len = 0; s.mel_n = -1; s.mel_dropped = 0; s.inc_valid = false;
     WLK_API_END
 }
 int wlk_session_audio_len(wlk_engine* e, int32_t sid, int64_t* n) {
@@ -1298,6 +1493,21 @@ int wlk_encode(wlk_engine* e, const int32_t* sids, int n, int32_t* content_out) 
     LOCK(e);
     WLK_CHECK(sids && content_out, "null argument");
     encode_batch(e, sids, n, content_out);
+    WLK_API_END
+}
+int wlk_encode_incremental(wlk_engine* e, const int32_t* sids, int n, int32_t* content_out, int32_t* block_rows_out) {
+    WLK_API_BEGIN
+    LOCK(e);
+    WLK_CHECK(sids && content_out, "null argument");
+    WLK_CHECK(e->finalized, "weights not finalized");
+    encode_incremental(e, sids, n, content_out, block_rows_out);
+    WLK_API_END
+}
+int wlk_session_reset_incremental(wlk_engine* e, int32_t sid) {
+    WLK_API_BEGIN
+    LOCK(e);
+    Session& s = get_root_session(e, sid, "the encoder K/V");
+    s.inc_valid = false;                       // the next incremental encode takes the whole window as its block
     WLK_API_END
 }
 int wlk_decode(wlk_engine* e, const int32_t* sids, int n, const int32_t* tokens, const int32_t* offsets, int32_t sot_index) {
@@ -1536,7 +1746,9 @@ int wlk_read_encoder(wlk_engine* e, int32_t sid, float* out) {
     convert_to_f32(s.xa, e->act, e->x, (int64_t)n, e->st);
     CUDA_CHECK(cudaMemcpyAsync(h, e->x, n * 4, cudaMemcpyDeviceToHost, e->st));
     CUDA_CHECK(cudaStreamSynchronize(e->st));
-    memcpy(out, h, n * 4);
+    const size_t dd = e->dims.n_audio_state, head = (size_t)(N_CTX - s.rot) * dd;      // ring slot -> logical position
+    memcpy(out, h + (size_t)s.rot * dd, head * 4);
+    memcpy(out + head, h, (n - head) * 4);
     WLK_API_END
 }
 int wlk_read_logits(wlk_engine* e, int32_t sid, int32_t which, float* out) {

@@ -1012,6 +1012,8 @@ align_rows_kernel(const LogitJob* __restrict__ jobs, int n_align, int n_text_ctx
             int g = f + j - 3;
             if (g < 0) g = -g;                           // reflect (no edge repeat), F.pad(mode="reflect")
             if (g >= N_CTX) g = 2 * (N_CTX - 1) - g;
+            g += job.rot;                                // ring-addressed encoder output (0 in parity mode)
+            if (g >= N_CTX) g -= N_CTX;
             v[j] = (p[g] - st[g * 2]) * st[g * 2 + 1];
         }
         acc += median7(v);
@@ -1057,6 +1059,88 @@ void align_reduce(const LogitJob* jobs, int n, int n_align, int n_text_ctx, Step
     CUDA_CHECK(cudaGetLastError());
 }
 
+
+// =====================================================================================
+// incremental encoder helpers (engine.cu encode_incremental)
+// =====================================================================================
+// conv1 operand rows of a block: frame f in [2 p0 - 1, 2 p1) reads mel rows f .. f + 2 of the padded time-major buffer
+// (row 0 is the zero pad row, frame f sits at row f + 1); frames outside [0, 3000) give zero rows (conv2's padding)
+template <typename T>
+__global__ void inc_gather_conv1_kernel(const IncJob* __restrict__ jobs, int n_mels, T* __restrict__ A1) {
+    const IncJob job = jobs[blockIdx.y];
+    const int nr = 2 * (job.p1 - job.p0) + 1, r = blockIdx.x;
+    if (r >= nr) return;
+    const int f = 2 * job.p0 - 1 + r, K = 3 * n_mels;
+    T* dst = A1 + (int64_t)(job.row1_off + r) * K;
+    const T* src = reinterpret_cast<const T*>(job.mel) + (int64_t)f * n_mels;    // rows f .. f + 2 are contiguous
+    const bool ok = f >= 0 && f < N_FRAMES;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) dst[i] = ok ? src[i] : from_f32<T>(0.f);
+}
+void inc_gather_conv1(const IncJob* jobs, int n, int max_rows1, int n_mels, void* A1, int type, cudaStream_t st) {
+    if (type == DT_BF16) inc_gather_conv1_kernel<bf16><<<dim3(max_rows1, n), 128, 0, st>>>(jobs, n_mels, (bf16*)A1);
+    else inc_gather_conv1_kernel<float><<<dim3(max_rows1, n), 128, 0, st>>>(jobs, n_mels, (float*)A1);
+    CUDA_CHECK(cudaGetLastError());
+}
+// conv2 operand rows: position p reads conv1 frames 2 p - 1 .. 2 p + 1 = packed conv1 rows 2 (p - p0) .. + 2 (contiguous);
+// conv1 rows of frames outside the window are conv2's zero padding.  Also the row maps and the positional rows (by slot).
+template <typename T>
+__global__ void inc_gather_conv2_kernel(const IncJob* __restrict__ jobs, int d, const T* __restrict__ H1, T* __restrict__ A2,
+                                        const float* __restrict__ enc_pos, float* __restrict__ posbuf, int32_t* __restrict__ row_slot,
+                                        int32_t* __restrict__ row_pos) {
+    const IncJob job = jobs[blockIdx.y];
+    const int r = blockIdx.x;
+    if (r >= job.p1 - job.p0) return;
+    const int p = job.p0 + r;
+    int slot = p + job.rot;
+    if (slot >= N_CTX) slot -= N_CTX;
+    const int64_t row = job.row_off + r;
+    for (int k = 0; k < 3; ++k) {
+        const int f = 2 * p - 1 + k;
+        const bool ok = f >= 0 && f < N_FRAMES;
+        const T* src = H1 + (int64_t)(job.row1_off + 2 * r + k) * d;
+        T* dst = A2 + row * 3 * d + (int64_t)k * d;
+        for (int i = threadIdx.x; i < d; i += blockDim.x) dst[i] = ok ? src[i] : from_f32<T>(0.f);
+    }
+    for (int i = threadIdx.x; i < d; i += blockDim.x) posbuf[row * d + i] = enc_pos[(int64_t)slot * d + i];
+    if (threadIdx.x == 0) { row_slot[row] = blockIdx.y; row_pos[row] = slot; }
+}
+void inc_gather_conv2(const IncJob* jobs, int n, int max_rows, int d, const void* H1, void* A2, const float* enc_pos, float* posbuf,
+                      int32_t* row_slot, int32_t* row_pos, int type, cudaStream_t st) {
+    if (type == DT_BF16) inc_gather_conv2_kernel<bf16><<<dim3(max_rows, n), 256, 0, st>>>(jobs, d, (const bf16*)H1, (bf16*)A2, enc_pos, posbuf, row_slot, row_pos);
+    else inc_gather_conv2_kernel<float><<<dim3(max_rows, n), 256, 0, st>>>(jobs, d, (const float*)H1, (float*)A2, enc_pos, posbuf, row_slot, row_pos);
+    CUDA_CHECK(cudaGetLastError());
+}
+template <typename T>
+__global__ void inc_scatter_rows_kernel(const IncJob* __restrict__ jobs, int d, const T* __restrict__ src) {
+    const IncJob job = jobs[blockIdx.y];
+    const int r = blockIdx.x;
+    if (r >= job.p1 - job.p0) return;
+    int slot = job.p0 + r + job.rot;
+    if (slot >= N_CTX) slot -= N_CTX;
+    const T* s = src + (int64_t)(job.row_off + r) * d;
+    T* dst = reinterpret_cast<T*>(job.xa) + (int64_t)slot * d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) dst[i] = s[i];
+}
+void inc_scatter_rows(const IncJob* jobs, int n, int max_rows, int d, const void* src, int type, cudaStream_t st) {
+    if (type == DT_BF16) inc_scatter_rows_kernel<bf16><<<dim3(max_rows, n), 256, 0, st>>>(jobs, d, (const bf16*)src);
+    else inc_scatter_rows_kernel<float><<<dim3(max_rows, n), 256, 0, st>>>(jobs, d, (const float*)src);
+    CUDA_CHECK(cudaGetLastError());
+}
+template <typename T>
+__global__ void copy_plane_rows_kernel(T* __restrict__ dst, const T* __restrict__ src, int lo, int cnt) {
+    const int64_t plane = (int64_t)blockIdx.x * N_CTX * 64;
+    for (int i = threadIdx.x; i < cnt * 64; i += blockDim.x) {
+        int row = lo + i / 64;
+        if (row >= N_CTX) row -= N_CTX;
+        dst[plane + (int64_t)row * 64 + (i & 63)] = src[plane + (int64_t)row * 64 + (i & 63)];
+    }
+}
+void copy_plane_rows(void* dst, const void* src, int n_planes, int lo, int cnt, int type, cudaStream_t st) {
+    if (cnt <= 0) return;
+    if (type == DT_BF16) copy_plane_rows_kernel<bf16><<<n_planes, 256, 0, st>>>((bf16*)dst, (const bf16*)src, lo, cnt);
+    else copy_plane_rows_kernel<float><<<n_planes, 256, 0, st>>>((float*)dst, (const float*)src, lo, cnt);
+    CUDA_CHECK(cudaGetLastError());
+}
 
 // =====================================================================================
 // Word-timestamp kernels of the LocalAgreement path: native replacements of the reference's two Triton

@@ -49,6 +49,24 @@ void mel_import(const float* mel_dev /*[n_mels,3000]*/, void* out /*[3002,n_mels
 
 void zero_rows(void* base, int type, int64_t row_elems, const int64_t* row_index_dev, int n_rows, cudaStream_t st);
 
+// incremental encoder (engine.cu encode_incremental): operand gathers for the conv stem over a block of positions, and
+// row scatters into a session's ring-addressed buffers
+struct IncJob {                 // one per session in the batch (device array)
+    const void* mel;            // [MEL_ROWS][n_mels] time-major log-mel of the window (activation type, zero pad rows)
+    void* xa;                   // session encoder output [1500][d]
+    int32_t p0, p1;             // block of logical positions [p0, p1)
+    int32_t rot;                // slot = (position + rot) % 1500
+    int32_t row1_off;           // first conv1 row of the block in the packed buffers (frames 2 p0 - 1 .. 2 p1 - 1)
+    int32_t row_off;            // first position row of the block in the packed buffers
+    int32_t pad;
+};
+void inc_gather_conv1(const IncJob* jobs, int n, int max_rows1, int n_mels, void* A1, int type, cudaStream_t st);
+void inc_gather_conv2(const IncJob* jobs, int n, int max_rows, int d, const void* H1, void* A2, const float* enc_pos, float* posbuf,
+                      int32_t* row_slot, int32_t* row_pos, int type, cudaStream_t st);
+void inc_scatter_rows(const IncJob* jobs, int n, int max_rows, int d, const void* src, int type, cudaStream_t st);
+// rows [lo, lo + cnt) (mod 1500) of every [1500][64] plane: dst plane <- src plane (template refresh of vacated slots)
+void copy_plane_rows(void* dst, const void* src, int n_planes, int lo, int cnt, int type, cudaStream_t st);
+
 void layernorm(const float* x, int64_t ldx, const float* w, const float* b, void* out, int out_type, int64_t ldo,
                int rows, int d, const int32_t* row_index_dev, cudaStream_t st);
 
@@ -101,6 +119,8 @@ struct LogitJob {               // one per session (device array)
     int32_t row_begin, row_end; // retained alignment rows [begin, end)
     int32_t content_len;
     int32_t full;               // 1: produce every retained row (debug tap); 0: last row only
+    int32_t rot;                // ring offset of the encoder output (incremental encoder): frame f sits in slot (f + rot) % 1500
+    int32_t pad;
 };
 struct StepResult { int32_t token; float logprob; int32_t frame; float no_speech; };
 

@@ -141,11 +141,25 @@ class WhisperEngine:
             raise ValueError("sids and source_indices differ in length")
         L.check(self.lib.wlk_sessions_gather_decoder(self.h, _ptr(a), _ptr(b), len(a)))
 
-    def encode(self, sids: Sequence[int]) -> List[int]:
+    incremental_encoder = False     # engine-wide default of ``encode``: True selects the labelled approximate mode
+
+    def encode(self, sids: Sequence[int], incremental: Optional[bool] = None) -> List[int]:
+        """AlignAtt._encode for a batch of sessions.  incremental=True (default: ``self.incremental_encoder``): the
+        labelled approximate mode that retains the encoder K/V across chunks and runs only the appended frames
+        (wlk_encode_incremental); the rows it encoded per session are left in ``self.last_block_rows``."""
         s = _i32(sids)
         out = np.zeros(len(s), np.int32)
-        L.check(self.lib.wlk_encode(self.h, _ptr(s), len(s), _ptr(out)))
+        if self.incremental_encoder if incremental is None else incremental:
+            rows = np.zeros(len(s), np.int32)
+            L.check(self.lib.wlk_encode_incremental(self.h, _ptr(s), len(s), _ptr(out), _ptr(rows)))
+            self.last_block_rows = [int(v) for v in rows]
+        else:
+            L.check(self.lib.wlk_encode(self.h, _ptr(s), len(s), _ptr(out)))
         return [int(v) for v in out]
+
+    def reset_incremental(self, sid: int) -> None:
+        """The next incremental encode of this session takes the whole window as its block (bounds the drift)."""
+        L.check(self.lib.wlk_session_reset_incremental(self.h, int(sid)))
 
     def decode(self, sids: Sequence[int], tokens: Sequence[Sequence[int]], sot_index: int = 0) -> None:
         s = _i32(sids)

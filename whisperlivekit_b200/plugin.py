@@ -61,7 +61,7 @@ def make_b200_alignatt_class():
 
 
 def install(precision: str = "bf16", device: int = 0, max_sessions: int = 64, max_batch: int = 64,
-            batching: bool = True, max_wait_s: float = 0.002, engine_factory=None):
+            batching: bool = True, max_wait_s: float = 0.002, engine_factory=None, incremental_encoder: bool = False):
     """Route WhisperLiveKit's SimulStreaming backend through the B200 engine (call once, before
     TranscriptionEngine is constructed).  With ``batching`` the per-session calls of the worker threads
     (audio_processor.py:543-551) are coalesced into batched C-ABI calls by batching.BatchingEngine.
@@ -83,6 +83,8 @@ def install(precision: str = "bf16", device: int = 0, max_sessions: int = 64, ma
         else:
             eng = engine_from_torch_whisper(torch_model, precision=precision, device=device,
                                             max_sessions=max_sessions, max_batch=max_batch)
+            # the labelled approximate mode (engine.encode docstring): retained encoder K/V, ~29 positions per chunk
+            eng.incremental_encoder = bool(incremental_encoder)
         if batching:
             from .batching import BatchingEngine
             eng = BatchingEngine(eng, max_batch=max_batch, max_wait_s=max_wait_s)
