@@ -124,3 +124,35 @@ def test_ring_rotation_equals_physically_shifted_buffers():
     xa_first = b.read_encoder(sb)
     assert np.abs(xa_ring[: 1500 - 100 - 2] - xa_first[100: 1500 - 2]).max() == 0.0
     a.close(); b.close()
+
+
+def test_alignment_reduction_reads_through_the_ring_offset():
+    """After slides (rot != 0) the processed attention the policy's argmax runs on (wlk_read_align_attn, logical frame
+    order) must equal the reference's _process_cross_attention (simul_whisper.py:390-433: z-score over tokens, median-7 with
+    reflect padding along FRAMES, mean over heads) applied to the raw rows brought back into logical order by hand."""
+    from whisperlivekit_b200.weights import synthetic_audio
+    dims, a, b = _engines()
+    b.close()
+    audio = synthetic_audio(36.0, seed=21)
+    s = a.open_session()
+    CH = 8000
+    a.append_audio(s, audio[: 60 * CH])
+    a.encode([s], incremental=True)
+    for k in range(60, 63):                                     # three slides: rot = 75
+        a.drop_audio(s, CH); a.append_audio(s, audio[k * CH:(k + 1) * CH])
+        a.encode([s], incremental=True)
+    rot = 75
+    prefix = list(a.specials.sot_sequence_including_notimestamps()) + [1169, 2068, 50, 999]
+    toks, frames, _ = _drive(a, s, prefix, steps=5)
+    raw = a.read_align_rows(s)                                  # [n_align, rows, 1500] by ring slot
+    got = a.read_align_attn(s)                                  # [rows, content] logical
+    logical = np.roll(raw, -rot, axis=-1).astype(np.float64)    # frame f sits in slot (f + rot) % 1500
+    z = (logical - logical.mean(axis=1, keepdims=True)) / (logical.std(axis=1, keepdims=True) + 1e-8)
+    pad = np.pad(z, ((0, 0), (0, 0), (3, 3)), mode="reflect")
+    win = np.stack([pad[..., j: j + 1500] for j in range(7)], axis=-1)
+    want = np.median(win, axis=-1).mean(axis=0)[:, : got.shape[1]]
+    # the tap holds the rows of the last 16-iteration window: here every row
+    assert got.shape[0] == want.shape[0]
+    assert np.abs(got - want).max() < 2e-3
+    assert frames[-1] == int(np.argmax(want[-1]))
+    a.close()
