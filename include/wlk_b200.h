@@ -216,6 +216,9 @@ typedef struct {
     int32_t left_context_steps;  /* K/V kept per layer (causal.py:103-106) */
     int32_t block_bidirectional; /* 1: queries see their whole block (causal.py:336-341) */
     int32_t conv_out_bias;
+    int32_t mutable_tail_steps;  /* bounded mutable tail (causal.py:101-113, _encode_mutable_tail :548-640): > 0 requires
+                                  * block_frames == 0; every call re-encodes the tail steps together with the new ones over
+                                  * the frozen K/V prefix and returns hidden rows for ALL of them                          */
 } wlk_qwen_dims;
 
 int wlk_qwen_create(const wlk_qwen_dims* dims, const wlk_config* cfg, wlk_qwen** out);
@@ -228,6 +231,8 @@ int wlk_qwen_session_open(wlk_qwen* q, int32_t* sid);
 int wlk_qwen_session_close(wlk_qwen* q, int32_t sid);
 int wlk_qwen_session_reset(wlk_qwen* q, int32_t sid);
 int wlk_qwen_session_state(wlk_qwen* q, int32_t sid, int32_t* pending_frames, int64_t* emitted_steps);
+/* QwenAudioCausalKVState.mutable_steps (causal.py:53-57): steps of the bounded mutable tail; emitted_steps counts frozen ones */
+int wlk_qwen_session_mutable_steps(wlk_qwen* q, int32_t sid, int32_t* mutable_steps);
 /* forward_chunk (causal.py:713-782) for n sessions at once.  mels_host holds the new mel frames of all sessions
  * back to back ([frames][n_mels] fp32, session i = rows frame_offsets[i] .. frame_offsets[i+1]); every complete
  * block (or chunk) is encoded; the newly emitted rows [steps][out_dim] of session i land in

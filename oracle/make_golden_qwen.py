@@ -76,9 +76,11 @@ def reference_encoder(dims, sd):
     from qwen3_asr_causal.config import RealtimeAudioConfig
     cfg = RealtimeAudioConfig(d_model=dims.out_dim, qwen_audio_block_bidirectional=dims.block_bidirectional,
                               qwen_audio_block_frames=dims.block_frames,
-                              qwen_audio_left_context_sec=dims.left_context_steps * 0.08)
+                              qwen_audio_left_context_sec=dims.left_context_steps * 0.08,
+                              qwen_audio_mutable_tail_sec=dims.mutable_tail_steps * 0.08)
     enc = QwenAudioCausalKVEncoder(GeometryTower(dims, sd).eval(), cfg).eval()
     assert enc.left_context_steps == dims.left_context_steps, (enc.left_context_steps, dims.left_context_steps)
+    assert enc.mutable_tail_steps == dims.mutable_tail_steps, (enc.mutable_tail_steps, dims.mutable_tail_steps)
     return enc
 
 
@@ -94,24 +96,30 @@ def mel_stream(n_frames, n_mels=128, seed=0):
 SCHEDULE = [25, 25, 7, 135, 0, 192, 400, 1, 183, 96, 600, 25]
 
 
+TAIL_SCHEDULE = [25, 25, 7, 135, 0, 192, 400, 1, 183, 96, 25, 3, 64, 25]
+
+
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
-    for name in ("qnano", "qnano-chunk"):
+    for name in ("qnano", "qnano-chunk", "qnano-tail", "qnano-tail-bidir"):
         dims = QWEN_DIMS[name]
         sd = synthetic_tower_state_dict(dims, seed=11)
         enc = reference_encoder(dims, sd)
-        mels = mel_stream(sum(SCHEDULE), dims.n_mels, seed=3)
+        # a mutable tail re-encodes tail + new steps in ONE piece: appends stay below the engine's 128 steps per call
+        schedule = SCHEDULE if dims.mutable_tail_steps == 0 else TAIL_SCHEDULE
+        mels = mel_stream(sum(schedule), dims.n_mels, seed=3)
         state = enc.init_state()
-        rec = dict(schedule=np.asarray(SCHEDULE, np.int64))
+        rec = dict(schedule=np.asarray(schedule, np.int64))
         a = 0
         with torch.no_grad():
-            for i, n in enumerate(SCHEDULE):
+            for i, n in enumerate(schedule):
                 hidden, state = enc.forward_chunk(torch.from_numpy(mels[a: a + n])[None], state)
                 a += n
                 h = hidden[0].numpy()
                 rec[f"steps{i}"] = np.asarray(h.shape[0], np.int64)
                 rec[f"emitted{i}"] = np.asarray(state.emitted_steps, np.int64)
                 rec[f"pending{i}"] = np.asarray(state.pending_frames, np.int64)
+                rec[f"mutable{i}"] = np.asarray(state.mutable_steps, np.int64)
                 rec[f"cache_len{i}"] = np.asarray(0 if state.layer_caches[0].key is None else state.layer_caches[0].key.shape[-2], np.int64)
                 if h.size:
                     flat = h.reshape(-1)

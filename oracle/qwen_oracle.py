@@ -42,14 +42,14 @@ class QwenTowerOracle:
     def open_session(self) -> int:
         sid = self._next
         self._next += 1
-        self._s[sid] = dict(buf=torch.zeros(0, self.dims.n_mels), caches=[None] * self.dims.n_layer, emitted=0)
+        self._s[sid] = dict(buf=torch.zeros(0, self.dims.n_mels), caches=[None] * self.dims.n_layer, emitted=0, tail=[], mutable=0)
         return sid
 
     def close_session(self, sid: int) -> None:
         self._s.pop(sid)
 
     def reset_session(self, sid: int) -> None:
-        self._s[sid] = dict(buf=torch.zeros(0, self.dims.n_mels), caches=[None] * self.dims.n_layer, emitted=0)
+        self._s[sid] = dict(buf=torch.zeros(0, self.dims.n_mels), caches=[None] * self.dims.n_layer, emitted=0, tail=[], mutable=0)
 
     # incremental log-mel front end behind the same method names as QwenTowerEngine (features.py:32-112)
     def load_mel_filters(self, filters=None) -> None:
@@ -73,6 +73,9 @@ class QwenTowerOracle:
 
     def pending_frames(self, sid: int) -> int:
         return int(self._s[sid]["buf"].shape[0])
+
+    def mutable_steps(self, sid: int) -> int:
+        return int(self._s[sid].get("mutable", 0))
 
     def emitted_steps(self, sid: int) -> int:
         return int(self._s[sid]["emitted"])
@@ -98,7 +101,7 @@ class QwenTowerOracle:
         x = F.linear(x.permute(0, 3, 1, 2).contiguous().view(b, t, c * f), W["conv_out.weight"], W.get("conv_out.bias"))
         return x[0] + self._pos(position, t)
 
-    def _layer(self, i: int, h: torch.Tensor, cache, position: int):               # causal.py:292-421
+    def _layer(self, i: int, h: torch.Tensor, cache, position: int, full_kv: bool = False):   # causal.py:292-421 (423-546 with full_kv)
         W, D = self.W, self.dims
         p = f"layers.{i}."
         n = h.shape[0]
@@ -123,7 +126,7 @@ class QwenTowerOracle:
         scores = scores.masked_fill(~allowed[None], torch.finfo(torch.float32).min)
         ctx = torch.matmul(F.softmax(scores, dim=-1), v).transpose(0, 1).contiguous().view(n, D.d_model)
         h = h + F.linear(ctx, W[p + "self_attn.out_proj.weight"], W[p + "self_attn.out_proj.bias"])
-        keep = min(total, D.left_context_steps)
+        keep = total if full_kv else min(total, D.left_context_steps)      # _attention_tail hands all keys of the call back
         new_cache = (k[:, -keep:].clone(), v[:, -keep:].clone())
         y = F.layer_norm(h, (D.d_model,), W[p + "final_layer_norm.weight"], W[p + "final_layer_norm.bias"], 1e-5)
         y = F.gelu(F.linear(y, W[p + "fc1.weight"], W[p + "fc1.bias"]))
@@ -147,6 +150,43 @@ class QwenTowerOracle:
         s["emitted"] += h.shape[0]
         return h
 
+    def _encode_mutable_tail(self, s: dict, ready: torch.Tensor) -> torch.Tensor:  # causal.py:548-640 (+ :423-546)
+        """Recompute the mutable tail plus the new chunks over the frozen K/V prefix WITHOUT touching the caches, return
+        the hidden rows of all of them, then freeze leading chunks until the tail fits ``mutable_tail_steps``."""
+        W, D = self.W, self.dims
+        tail = s.setdefault("tail", [])
+        blocks = list(tail) + [ready[a: a + D.chunk_frames] for a in range(0, ready.shape[0], D.chunk_frames)]
+        if not blocks:
+            return torch.zeros(0, D.out_dim)
+        position = s["emitted"]
+        hs, step, steps = [], position, []
+        for b in blocks:
+            c = self._conv_chunk(b, step)
+            hs.append(c); steps.append(c.shape[0]); step += c.shape[0]
+        h = torch.cat(hs, dim=0)
+        all_kv = []
+        for i in range(D.n_layer):
+            h, kv = self._layer(i, h, s["caches"][i], position, full_kv=True)   # [frozen cache + every key of the call]; cache untouched
+            all_kv.append(kv)
+        h = F.layer_norm(h, (D.d_model,), W["ln_post.weight"], W["ln_post.bias"], 1e-5)
+        h = F.gelu(F.linear(h, W["proj1.weight"], W["proj1.bias"]))
+        h = F.linear(h, W["proj2.weight"], W["proj2.bias"])
+        total_steps = sum(steps)
+        freeze_steps = freeze_blocks = 0
+        while freeze_blocks < len(blocks) and total_steps - freeze_steps - steps[freeze_blocks] >= D.mutable_tail_steps:
+            freeze_steps += steps[freeze_blocks]; freeze_blocks += 1
+        if freeze_steps > 0:
+            drop = total_steps - freeze_steps                      # the newest keys stay mutable: not in the cache (:628-637)
+            for i in range(D.n_layer):
+                k_all, v_all = all_kv[i]
+                end = k_all.shape[1] - drop
+                keep = min(end, D.left_context_steps)
+                s["caches"][i] = (k_all[:, end - keep: end].clone(), v_all[:, end - keep: end].clone())
+            s["emitted"] += freeze_steps
+        s["tail"] = blocks[freeze_blocks:]
+        s["mutable"] = total_steps - freeze_steps
+        return h
+
     # -- the entry point ---------------------------------------------------------------
     @torch.no_grad()
     def forward_chunk(self, sids: Sequence[int], mels: Sequence[np.ndarray]) -> List[np.ndarray]:
@@ -157,10 +197,16 @@ class QwenTowerOracle:
         for sid, m in zip(sids, mels):
             s = self._s[sid]
             m = _t(np.asarray(m, np.float32).reshape(-1, D.n_mels))
+            if m.shape[0] == 0:                                    # causal.py:731-736: an empty append touches nothing
+                out.append(np.zeros((0, D.out_dim), np.float32))
+                continue
             buf = torch.cat([s["buf"], m], dim=0)
             consume = D.block_frames if D.block_frames > 0 else D.chunk_frames
             ready = (buf.shape[0] // consume) * consume
             s["buf"] = buf[ready:].clone()
+            if getattr(D, "mutable_tail_steps", 0) > 0:
+                out.append(self._encode_mutable_tail(s, buf[:ready]).numpy())
+                continue
             if ready == 0:
                 out.append(np.zeros((0, D.out_dim), np.float32))
                 continue

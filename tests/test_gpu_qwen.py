@@ -13,7 +13,7 @@ from test_oracle_qwen import check_stream, qwen_case
 from whisperlivekit_b200.qwen_dims import QWEN_DIMS, synthetic_tower_state_dict
 
 
-@pytest.mark.parametrize("name", ["qnano", "qnano-chunk"])
+@pytest.mark.parametrize("name", ["qnano", "qnano-chunk", "qnano-tail", "qnano-tail-bidir"])
 def test_fp32_tower_matches_reference_fixtures(name):
     from whisperlivekit_b200.qwen_engine import QwenTowerEngine
     g, dims, sd, mels, sched = qwen_case(name)
@@ -22,7 +22,7 @@ def test_fp32_tower_matches_reference_fixtures(name):
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["qnano", "qnano-chunk"])
+@pytest.mark.parametrize("name", ["qnano", "qnano-chunk", "qnano-tail", "qnano-tail-bidir"])
 def test_bf16_tower_close_to_reference_fixtures(name):
     from whisperlivekit_b200.qwen_engine import QwenTowerEngine
     g, dims, sd, mels, sched = qwen_case(name)

@@ -31,6 +31,8 @@ def check_stream(engine, g, mels, sched, tol):
         assert h.shape[0] == int(g[f"steps{i}"]), f"call {i}: emitted rows"
         assert engine.emitted_steps(sid) == int(g[f"emitted{i}"])
         assert engine.pending_frames(sid) == int(g[f"pending{i}"])
+        if f"mutable{i}" in g:
+            assert engine.mutable_steps(sid) == int(g[f"mutable{i}"]), f"call {i}: mutable tail"
         if h.size:
             flat = h.reshape(-1)
             worst = max(worst, float(np.abs(flat[g[f"idx{i}"]] - g[f"val{i}"]).max()))
@@ -46,7 +48,7 @@ def check_stream(engine, g, mels, sched, tol):
     return worst
 
 
-@pytest.mark.parametrize("name", ["qnano", "qnano-chunk"])
+@pytest.mark.parametrize("name", ["qnano", "qnano-chunk", "qnano-tail", "qnano-tail-bidir"])
 def test_oracle_matches_reference_fixtures(name):
     from oracle.qwen_oracle import QwenTowerOracle
     g, dims, sd, mels, sched = qwen_case(name)

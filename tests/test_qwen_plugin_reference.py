@@ -10,15 +10,17 @@ import torch
 pytestmark = pytest.mark.reference
 
 
-@pytest.mark.parametrize("name", ["qnano", "qnano-chunk"])
+@pytest.mark.parametrize("name", ["qnano", "qnano-chunk", "qnano-tail", "qnano-tail-bidir"])
 def test_drop_in_encoder_equals_reference(name):
     sys.path.insert(0, "/root/reference/third_party/qwen3-asr-causal/src")
-    from oracle.make_golden_qwen import SCHEDULE, mel_stream, reference_encoder
+    from oracle.make_golden_qwen import SCHEDULE, TAIL_SCHEDULE, mel_stream, reference_encoder
     from oracle.qwen_oracle import QwenTowerOracle
     from whisperlivekit_b200.qwen_dims import QWEN_DIMS, synthetic_tower_state_dict
     from whisperlivekit_b200.qwen_plugin import B200QwenAudioCausalKVEncoder
 
     dims = QWEN_DIMS[name]
+    if dims.mutable_tail_steps:
+        SCHEDULE = TAIL_SCHEDULE                                          # tail + new steps stay below 128 per call
     ref = reference_encoder(dims, synthetic_tower_state_dict(dims, seed=23))
     mine = B200QwenAudioCausalKVEncoder.from_reference(ref, engine_factory=lambda d, sd: QwenTowerOracle(d, sd))
     assert mine.dims == dims                                              # geometry recovered from the modules
@@ -33,7 +35,8 @@ def test_drop_in_encoder_equals_reference(name):
             assert hm.shape == hr.shape
             if hr.numel():
                 assert float((hm - hr).abs().max()) < 2e-5
-            for f in ("frames_seen", "emitted_steps", "pending_frames", "last_input_frames", "last_recomputed_frames"):
+            for f in ("frames_seen", "emitted_steps", "pending_frames", "last_input_frames", "last_recomputed_frames",
+                      "last_recomputed_context_frames", "mutable_steps"):
                 assert getattr(sm, f) == getattr(sr, f), f
         hr, sr = ref.flush_pending(sr)
         hm, sm = mine.flush_pending(sm)

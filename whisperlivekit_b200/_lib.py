@@ -21,7 +21,7 @@ class wlk_dims(C.Structure):
 class wlk_qwen_dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "n_mels", "conv_channels", "d_model", "n_head", "n_layer", "ffn_dim", "out_dim", "max_positions",
-        "chunk_frames", "block_frames", "left_context_steps", "block_bidirectional", "conv_out_bias")]
+        "chunk_frames", "block_frames", "left_context_steps", "block_bidirectional", "conv_out_bias", "mutable_tail_steps")]
 
 
 class wlk_sf_dims(C.Structure):
@@ -79,6 +79,7 @@ SIGNATURES = {
     "wlk_qwen_session_close": (C.c_int, [_vp, C.c_int32]),
     "wlk_qwen_session_reset": (C.c_int, [_vp, C.c_int32]),
     "wlk_qwen_session_state": (C.c_int, [_vp, C.c_int32, _vp, _vp]),
+    "wlk_qwen_session_mutable_steps": (C.c_int, [_vp, C.c_int32, _vp]),
     "wlk_qwen_forward_chunk": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int64, _vp]),
     "wlk_qwen_append_audio": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int64, _vp, C.c_int32]),
     "wlk_qwen_flush_pending": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int64, _vp]),

@@ -188,6 +188,7 @@ constexpr int QMEL_AUDIO_CAP = QMEL_MAX_FRAMES * HOP + 2 * N_FFT;
 struct QSession {
     bool open = false;
     std::vector<float> pending;         // mel frames not yet consumed (host: the caller hands mels on the host)
+    std::vector<float> tail;            // bounded mutable tail: the mel chunks of the steps that are still re-computable
     int64_t emitted = 0;                // encoder steps emitted so far == absolute position of the next step
     void* kv = nullptr;
     // incremental log-mel front end (reference features.py:32-112): the sample window lives on the device
@@ -389,6 +390,8 @@ void create(const wlk_qwen_dims* dims, const wlk_config* cfg, wlk_qwen** out) {
     WLK_CHECK(D.d_model % 64 == 0 && D.d_model / D.n_head == 64 && D.d_model <= 1280, "heads must be 64 wide, d_model <= 1280");
     WLK_CHECK(D.conv_channels % 8 == 0, "conv_channels must be a multiple of 8");
     WLK_CHECK(D.block_frames % 8 == 0 && D.block_frames / 8 <= Q_STEPS_CAP, "block_frames must be a multiple of 8 and <= %d", 8 * Q_STEPS_CAP);
+    WLK_CHECK(D.mutable_tail_steps >= 0 && D.mutable_tail_steps < Q_STEPS_CAP, "mutable_tail_steps must be in [0, %d)", Q_STEPS_CAP);
+    WLK_CHECK(D.mutable_tail_steps == 0 || D.block_frames == 0, "fixed attention blocks and a mutable tail are exclusive");   // causal.py:127-131
     WLK_CHECK(D.left_context_steps >= 1 && D.left_context_steps + Q_STEPS_CAP <= 512, "left_context_steps must be in [1, %d]", 512 - Q_STEPS_CAP);
     WLK_CHECK(cfg->max_sessions >= 1 && cfg->max_batch >= 1, "max_sessions / max_batch must be >= 1");
     int ndev = 0;
@@ -570,26 +573,43 @@ void forward_chunk(wlk_qwen* q, const int32_t* sids, int n, const float* mels, c
     WLK_CHECK(n >= 1 && n <= q->cfg.max_batch, "batch %d outside [1, %d]", n, q->cfg.max_batch);
     const int consume = (D.block_frames > 0 && !flush) ? D.block_frames : 8;
     const int steps_cap = (D.block_frames > 0 && !flush) ? D.block_frames / 8 : Q_STEPS_CAP;
-    // append, split off what is ready (reference forward_chunk: causal.py:742-752)
-    std::vector<std::vector<float>> ready(n);
-    std::vector<int> done_steps(n, 0), total_steps(n, 0);
+    // append, split off what is ready (reference forward_chunk: causal.py:742-752).  Nothing of a session is committed
+    // before the whole call has been validated and run: `rest` / `new_tail` replace pending / tail at the end.
+    const int M = flush ? 0 : D.mutable_tail_steps;
+    std::vector<std::vector<float>> ready(n), rest(n), new_tail(n);
+    std::vector<int> done_steps(n, 0), total_steps(n, 0), freeze(n, 0);
     int64_t rows_total = 0;
     for (int i = 0; i < n; ++i) {
         QSession& s = qsession(q, sids[i]);
         for (int j = 0; j < i; ++j) WLK_CHECK(sids[j] != sids[i], "session %d appears twice in the batch", sids[i]);
+        std::vector<float> all(s.pending);
         if (!flush) {
             const int nf = frame_off[i + 1] - frame_off[i];
             WLK_CHECK(nf >= 0, "negative frame count");
-            s.pending.insert(s.pending.end(), mels + (size_t)frame_off[i] * D.n_mels, mels + (size_t)frame_off[i + 1] * D.n_mels);
+            all.insert(all.end(), mels + (size_t)frame_off[i] * D.n_mels, mels + (size_t)frame_off[i + 1] * D.n_mels);
         }
-        const int have = (int)(s.pending.size() / D.n_mels);
+        const int have = (int)(all.size() / D.n_mels);
         const int take = have / consume * consume;
         if ((D.block_frames == 0 || flush) && D.block_bidirectional)
             WLK_CHECK(take / 8 <= Q_STEPS_CAP, "bidirectional attention over %d steps in one call exceeds %d", take / 8, Q_STEPS_CAP);
-        ready[i].assign(s.pending.begin(), s.pending.begin() + (size_t)take * D.n_mels);
-        s.pending.erase(s.pending.begin(), s.pending.begin() + (size_t)take * D.n_mels);
-        if (flush) s.pending.clear();                     // a sub-chunk remainder carries no decodable content (causal.py:697-705)
-        total_steps[i] = take / 8;
+        const bool empty_append = !flush && frame_off[i + 1] == frame_off[i];     // causal.py:731-736: touches nothing
+        if (M > 0 && empty_append) {
+            new_tail[i] = s.tail; total_steps[i] = 0; freeze[i] = 0;
+        } else if (M > 0) {
+            // _encode_mutable_tail (causal.py:548-640): the previously mutable chunks run again in front of the new ones,
+            // at positions emitted .. (emitted counts frozen steps only); one round, so that every step sees the call's keys
+            const int tail_steps = (int)(s.tail.size() / ((size_t)8 * D.n_mels));
+            ready[i] = s.tail;
+            ready[i].insert(ready[i].end(), all.begin(), all.begin() + (size_t)take * D.n_mels);
+            total_steps[i] = tail_steps + take / 8;
+            WLK_CHECK(total_steps[i] <= Q_STEPS_CAP, "mutable tail + new steps = %d exceed %d per call", total_steps[i], Q_STEPS_CAP);
+            freeze[i] = std::max(0, total_steps[i] - M);               // leading blocks frozen until the tail fits (:617-627)
+            new_tail[i].assign(ready[i].begin() + (size_t)freeze[i] * 8 * D.n_mels, ready[i].end());
+        } else {
+            ready[i].assign(all.begin(), all.begin() + (size_t)take * D.n_mels);
+            total_steps[i] = take / 8;
+        }
+        if (!flush) rest[i].assign(all.begin() + (size_t)take * D.n_mels, all.end());   // flush: a sub-chunk remainder carries no decodable content (causal.py:697-705)
         out_row_off[i] = (int32_t)rows_total;
         rows_total += total_steps[i];
     }
@@ -649,9 +669,14 @@ void forward_chunk(wlk_qwen* q, const int32_t* sids, int n, const float* mels, c
                                        (size_t)steps[k] * D.out_dim * 4, cudaMemcpyDeviceToHost, q->st));
             r += steps[k];
             done_steps[i] += steps[k];
-            q->sess[sids[i]].emitted += steps[k];
+            q->sess[sids[i]].emitted += M > 0 ? freeze[i] : steps[k];    // a mutable tail: only the frozen steps count (:638)
         }
         CUDA_CHECK(cudaStreamSynchronize(q->st));        // the staging block and outbuf are reused by the next round
+    }
+    for (int i = 0; i < n; ++i) {                        // commit the host-side buffers
+        QSession& s = q->sess[sids[i]];
+        s.pending.swap(rest[i]);
+        if (M > 0) s.tail.swap(new_tail[i]);
     }
 }
 
@@ -812,7 +837,7 @@ int wlk_qwen_session_open(wlk_qwen* q, int32_t* sid) {
     const size_t bytes = (size_t)q->dims.n_layer * 2 * q->dims.n_head * q->ring * 64 * q->es();
     CUDA_CHECK(cudaMalloc(&s.kv, bytes));
     q->bytes_sessions += bytes;
-    s.open = true; s.emitted = 0; s.pending.clear();
+    s.open = true; s.emitted = 0; s.pending.clear(); s.tail.clear();
     *sid = found;
     WLK_API_END
 }
@@ -834,7 +859,7 @@ int wlk_qwen_session_reset(wlk_qwen* q, int32_t sid) {
     WLK_API_BEGIN
     QLOCK(q);
     QSession& s = qsession(q, sid);
-    s.emitted = 0; s.pending.clear();
+    s.emitted = 0; s.pending.clear(); s.tail.clear();
     s.buf_len = s.buf_start_frame = s.mel_emitted = s.total_samples = 0;       // StreamingMelExtractor.reset, features.py:112
     WLK_API_END
 }
@@ -844,6 +869,14 @@ int wlk_qwen_session_state(wlk_qwen* q, int32_t sid, int32_t* pending_frames, in
     QSession& s = qsession(q, sid);
     if (pending_frames) *pending_frames = (int32_t)(s.pending.size() / q->dims.n_mels);
     if (emitted_steps) *emitted_steps = s.emitted;
+    WLK_API_END
+}
+int wlk_qwen_session_mutable_steps(wlk_qwen* q, int32_t sid, int32_t* mutable_steps) {
+    WLK_API_BEGIN
+    QLOCK(q);
+    QSession& s = qsession(q, sid);
+    WLK_CHECK(mutable_steps != nullptr, "null argument");
+    *mutable_steps = (int32_t)(s.tail.size() / ((size_t)8 * q->dims.n_mels));
     WLK_API_END
 }
 int wlk_qwen_forward_chunk(wlk_qwen* q, const int32_t* sids, int n, const float* mels_host, const int32_t* frame_offsets,

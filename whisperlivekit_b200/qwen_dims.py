@@ -23,6 +23,8 @@ class QwenTowerDims:
     left_context_steps: int = 150     # 12 s of left context in steps (causal.py:103-106)
     block_bidirectional: bool = True
     conv_out_bias: bool = True
+    mutable_tail_steps: int = 0       # bounded mutable tail (causal.py:101-113, 548-640): the last steps are re-encoded by
+                                      # every call until they leave the tail; 0 = strict append-only; exclusive with blocks
 
     @property
     def freq_out(self) -> int:
@@ -35,7 +37,7 @@ class QwenTowerDims:
     def as_tuple(self):
         return (self.n_mels, self.conv_channels, self.d_model, self.n_head, self.n_layer, self.ffn_dim, self.out_dim,
                 self.max_positions, self.chunk_frames, self.block_frames, self.left_context_steps,
-                int(self.block_bidirectional), int(self.conv_out_bias))
+                int(self.block_bidirectional), int(self.conv_out_bias), self.mutable_tail_steps)
 
 
 QWEN_DIMS: Dict[str, QwenTowerDims] = {
@@ -44,6 +46,13 @@ QWEN_DIMS: Dict[str, QwenTowerDims] = {
                            left_context_steps=30),
     "qnano-chunk": QwenTowerDims(conv_channels=8, d_model=128, n_head=2, n_layer=2, ffn_dim=256, out_dim=96,
                                  max_positions=4096, block_frames=0, left_context_steps=25, block_bidirectional=False),
+    # bounded mutable tail: the last 6 steps (0.48 s) stay re-computable; causal, and bidirectional within a call
+    "qnano-tail": QwenTowerDims(conv_channels=8, d_model=128, n_head=2, n_layer=2, ffn_dim=256, out_dim=96,
+                                max_positions=4096, block_frames=0, left_context_steps=25, block_bidirectional=False,
+                                mutable_tail_steps=6),
+    "qnano-tail-bidir": QwenTowerDims(conv_channels=8, d_model=128, n_head=2, n_layer=2, ffn_dim=256, out_dim=96,
+                                      max_positions=4096, block_frames=0, left_context_steps=25, block_bidirectional=True,
+                                      mutable_tail_steps=6),
     # Qwen3-ASR-0.6B audio tower (public HF audio_config: d_model 896, 18 layers, 14 heads, ffn 3584,
     # downsample_hidden_size 480, output_dim 1024); to be confirmed against the checkpoint when it is mounted
     "qwen3-asr-0.6b": QwenTowerDims(),

@@ -73,6 +73,12 @@ class QwenTowerEngine:
     def emitted_steps(self, sid: int) -> int:
         return self._state(sid)[1]
 
+    def mutable_steps(self, sid: int) -> int:
+        """steps of the bounded mutable tail (QwenAudioCausalKVState.mutable_steps); emitted_steps counts frozen steps"""
+        m = C.c_int32()
+        L.check(self.lib.wlk_qwen_session_mutable_steps(self.h, sid, C.byref(m)))
+        return m.value
+
     # -- forward_chunk (causal.py:713-782), batched over sessions -----------------------------
     def forward_chunk(self, sids: Sequence[int], mels: Sequence[np.ndarray]) -> List[np.ndarray]:
         n = len(sids)
@@ -85,6 +91,7 @@ class QwenTowerEngine:
         flat = np.concatenate(parts, axis=0) if offs[-1] else np.zeros((1, D.n_mels), np.float32)
         consume = D.block_frames if D.block_frames > 0 else D.chunk_frames
         cap = int(sum((self.pending_frames(s) + p.shape[0]) // consume * consume // D.chunk_frames for s, p in zip(sids, parts)))
+        cap += D.mutable_tail_steps * n                      # a mutable tail re-emits its steps with every call
         out = np.zeros((max(cap, 1), D.out_dim), np.float32)
         rows = np.zeros(n + 1, np.int32)
         ids = np.asarray(list(sids), np.int32)

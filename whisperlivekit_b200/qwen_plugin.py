@@ -51,7 +51,7 @@ class B200QwenAudioCausalKVEncoder:
         self.block_frames = dims.block_frames
         self.left_context_steps = dims.left_context_steps
         self.block_bidirectional = dims.block_bidirectional
-        self.mutable_tail_steps = 0
+        self.mutable_tail_steps = dims.mutable_tail_steps
 
     # -- construction from the reference object ----------------------------------------------------------
     @staticmethod
@@ -65,13 +65,11 @@ class B200QwenAudioCausalKVEncoder:
             max_positions=int(t.positional_embedding.positional_embedding.shape[0]),
             chunk_frames=int(ref_encoder.chunk_frames), block_frames=int(ref_encoder.block_frames),
             left_context_steps=int(ref_encoder.left_context_steps), block_bidirectional=bool(ref_encoder.block_bidirectional),
-            conv_out_bias=t.conv_out.bias is not None)
+            conv_out_bias=t.conv_out.bias is not None, mutable_tail_steps=int(getattr(ref_encoder, "mutable_tail_steps", 0)))
 
     @classmethod
     def from_reference(cls, ref_encoder, engine_factory=None, **engine_kw):
         """Pack the reference encoder's tower weights (its own state_dict names) into an engine."""
-        if getattr(ref_encoder, "mutable_tail_steps", 0):
-            raise NotImplementedError("the B200 tower runs the append-only regime (mutable tail off, config.py:99-104)")
         dims = cls.dims_of(ref_encoder)
         sd = {k: v.detach().float().cpu().numpy() for k, v in ref_encoder.audio_tower.state_dict().items()}
         if engine_factory is None:
@@ -93,6 +91,7 @@ class B200QwenAudioCausalKVEncoder:
     def _sync(self, state):
         state.emitted_steps = self.engine.emitted_steps(state.sid)
         state.pending_frames = self.engine.pending_frames(state.sid)
+        state.mutable_steps = self.engine.mutable_steps(state.sid) if self.mutable_tail_steps else 0
 
     def forward_chunk(self, mels, state: Optional[B200QwenAudioState] = None):
         import torch
@@ -108,10 +107,11 @@ class B200QwenAudioCausalKVEncoder:
         state.last_input_frames = n
         state.frames_seen += n
         before = self.engine.pending_frames(state.sid)
+        tail_frames = state.mutable_steps * self.chunk_frames if n else 0     # causal.py:753-760: tail mels run again
         h = self.engine.forward_chunk([state.sid], [mels[0].detach().float().cpu().numpy()])[0]
         self._sync(state)
-        state.last_recomputed_frames = before + n - state.pending_frames
-        state.last_recomputed_context_frames = 0
+        state.last_recomputed_frames = tail_frames + before + n - state.pending_frames if n else 0
+        state.last_recomputed_context_frames = tail_frames
         return torch.from_numpy(np.ascontiguousarray(h))[None].to(mels.device), state
 
     def flush_pending(self, state: B200QwenAudioState):
