@@ -145,6 +145,43 @@ def test_bf16_true_geometry_tracks_oracle_and_seam_objects():
     shared.close()
 
 
+def test_registration_through_the_reference_factory():
+    """plugin.install_sortformer(): the reference's unchanged core.online_diarization_factory (core.py:468-480) builds the
+    B200 drop-in although NeMo is absent (the real module would exit at import), a checkpoint-shaped state_dict with
+    NeMo's extra buffers loads, and audio_processor's calling convention works end to end."""
+    from oracle import stage_reference
+    if not stage_reference.staged():
+        pytest.skip("oracle/_ref not staged")
+    stage_reference.import_staged_reference()
+    import types
+    from whisperlivekit_b200 import plugin
+    from whisperlivekit_b200.sortformer_dims import SORTFORMER_DIMS, synthetic_sortformer_state_dict, synthetic_two_speaker_audio
+    d = SORTFORMER_DIMS["small"]
+    sd = dict(synthetic_sortformer_state_dict(d, 2))
+    sd["preprocessor.featurizer.window"] = np.zeros(400, np.float32)                  # buffers a .nemo state_dict also holds
+    sd["encoder.layers.0.conv.batch_norm.num_batches_tracked"] = np.asarray(7, np.int64)
+    sd["sortformer_modules.hidden_to_spks.weight"] = np.zeros((d.n_spk, 2 * d.tf_d_model), np.float32)
+    plugin.install_sortformer(state_dict=sd, dims=d, precision="fp32", max_sessions=2, max_batch=2)
+    try:
+        from whisperlivekit.core import online_diarization_factory
+        from whisperlivekit.diarization.sortformer_backend import SortformerDiarization
+        shared = SortformerDiarization(model_path=None)
+        args = types.SimpleNamespace(diarization_backend="sortformer", sortformer_max_speakers=2)
+        online = online_diarization_factory(args, shared)
+        assert hasattr(online, "buffer_audio") and online.max_speakers == 2
+        audio = synthetic_two_speaker_audio(2.5, seed=4)
+        got = []
+        for k in range(5):
+            online.insert_audio_chunk(audio[k * 8000:(k + 1) * 8000])
+            got.append(asyncio.run(online.diarize()))
+        assert got[0] == [] and got[2] == [] and len(got[1]) >= 1 and len(got[3]) >= 1
+        assert got[1][0].start == 0.0 and got[3][-1].end == 2.0 and all(0 <= s.speaker < 2 for s in got[1] + got[3])
+        online.insert_silence(1.5)
+        online.close(); shared.close()
+    finally:
+        plugin.uninstall_sortformer()
+
+
 def _read_device(ptr, n):
     import torch
 

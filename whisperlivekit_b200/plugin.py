@@ -110,3 +110,60 @@ def uninstall():
     if hasattr(be, "_b200_saved"):
         be.AlignAtt, be.SimulStreamingASR.load_model, be.SimulStreamingOnlineProcessor.__del__ = be._b200_saved
         del be._b200_saved
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# diarization seam
+# ---------------------------------------------------------------------------------------------------------------
+def sortformer_state_dict_from_nemo(path: str):
+    """Weights of a ``.nemo`` checkpoint (a tar archive holding ``model_weights.ckpt``, a plain torch state_dict under
+    NeMo's parameter names) as numpy arrays -- read without NeMo."""
+    import io
+    import tarfile
+
+    import torch
+    with tarfile.open(path, "r:*") as tar:
+        member = next(m for m in tar.getmembers() if m.name.endswith("model_weights.ckpt"))
+        blob = tar.extractfile(member).read()
+    sd = torch.load(io.BytesIO(blob), map_location="cpu", weights_only=True)
+    return {k: v.detach().float().cpu().numpy() for k, v in sd.items()}
+
+
+def install_sortformer(state_dict=None, dims=None, precision: str = "bf16", device: int = 0, max_sessions: int = 64,
+                       max_batch: int = 64):
+    """Route ``--diarization-backend sortformer`` through the B200 engine without editing WhisperLiveKit: core.py imports
+    ``SortformerDiarization`` / ``SortformerDiarizationOnline`` from ``whisperlivekit.diarization.sortformer_backend``
+    (core.py:297-299, 472-477), a module that exits at import when NeMo is missing (sortformer_backend.py:14-22).  This
+    puts a module of that name in ``sys.modules`` whose two classes are the B200 drop-ins, with the reference's constructor
+    signatures (``SortformerDiarization(model_name=..., model_path=...)``, ``SortformerDiarizationOnline(shared_model,
+    sample_rate, max_speakers)``).  Weights: ``state_dict`` (NeMo names), else ``model_path`` must point at a ``.nemo``."""
+    import sys
+    import types
+
+    from .sortformer_dims import SORTFORMER_DIMS
+    from .sortformer_engine import B200SortformerDiarization, B200SortformerDiarizationOnline
+    d = dims or SORTFORMER_DIMS["diar_streaming_sortformer_4spk-v2"]
+
+    class SortformerDiarization(B200SortformerDiarization):
+        def __init__(self, model_name: str = "nvidia/diar_streaming_sortformer_4spk-v2", model_path=None):
+            sd = state_dict
+            if sd is None:
+                if not model_path:
+                    raise FileNotFoundError("no network on this host: pass --sortformer-model-path <file.nemo> "
+                                            f"(cannot download {model_name})")
+                sd = sortformer_state_dict_from_nemo(model_path)
+            super().__init__(d, sd, precision=precision, device=device, max_sessions=max_sessions, max_batch=max_batch)
+
+    mod = types.ModuleType("whisperlivekit.diarization.sortformer_backend")
+    mod.SortformerDiarization = SortformerDiarization
+    mod.SortformerDiarizationOnline = B200SortformerDiarizationOnline
+    mod.__b200__ = True
+    sys.modules["whisperlivekit.diarization.sortformer_backend"] = mod
+    return mod
+
+
+def uninstall_sortformer():
+    import sys
+    m = sys.modules.get("whisperlivekit.diarization.sortformer_backend")
+    if m is not None and getattr(m, "__b200__", False):
+        del sys.modules["whisperlivekit.diarization.sortformer_backend"]

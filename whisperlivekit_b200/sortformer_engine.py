@@ -63,8 +63,11 @@ class SortformerEngine:
         full.setdefault("mel_filters", mel_filterbank(d.n_mels, 16000, d.n_fft))
         for name, arr in full.items():
             a = np.ascontiguousarray(arr, np.float32)
-            if a.ndim == 0:
-                continue                                    # BatchNorm's num_batches_tracked
+            # a NeMo checkpoint also carries buffers of modules this path replaces or never calls: the preprocessor's window /
+            # filterbank (the front end is rebuilt from the geometry), BatchNorm's counter, the unused hidden_to_spks layer
+            if (a.ndim == 0 or name.startswith(("preprocessor.", "sortformer_modules.hidden_to_spks."))
+                    or name.endswith("num_batches_tracked")):
+                continue
             shape = (C.c_int64 * a.ndim)(*a.shape)
             L.check(self.lib.wlk_sf_load_tensor(self.h, name.encode(), _ptr(a), shape, a.ndim))
         L.check(self.lib.wlk_sf_finalize_weights(self.h))
