@@ -181,6 +181,9 @@ int wlk_op_encoder_attention(wlk_engine* e, int backend, const void* qkv, int ty
  *      median_kernel / dtw_kernel (whisper/triton_ops.py:13-103) with the semantics of its CPU path
  *      (whisper/timing.py:19-54 median_filter; :57-105 dtw_cpu + backtrace).  x is device fp32.
  *      wlk_op_dtw: x[N tokens, M frames] -> alignment path (text_idx[i], time_idx[i]), i < *len <= N+M.   */
+/* diagnostic: the tcgen05 encoder attention with one CTA stamping clock64() at its pipeline hand-offs, [12 key tiles][8]:
+ * MMA warp before S_j / before P_j V, softmax warp after S ready / exponentials done / arrive (tools/attn_trace.py)      */
+int wlk_op_encoder_attention_trace(wlk_engine* e, const void* qkv_dev, int batch, void* out_dev, int64_t* stamps_host);
 int wlk_op_median_filter(wlk_engine* e, const float* x_dev, float* out_dev, int rows, int cols, int width);
 int wlk_op_dtw(wlk_engine* e, const float* x_dev, int N, int M, int32_t* text_idx_host, int32_t* time_idx_host,
                int32_t* len_out);

@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(ATT_THREADS, X3 ? 1 : 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_lo,
                const CUtensorMap* __restrict__ kv_maps,
                const DecJob* __restrict__ jobs, int layer, const int32_t* __restrict__ align_rank,
-               int n_head, int d_model, int kv_len, void* __restrict__ out_ptr) {
+               int n_head, int d_model, int kv_len, void* __restrict__ out_ptr, long long* __restrict__ trace = nullptr) {
+    // diagnostic (tools/attn_trace.py): one CTA in the middle of the grid stamps clock64() at its pipeline hand-offs
+    const bool tr = trace != nullptr && blockIdx.x == 3 && blockIdx.y == 1 && blockIdx.z == gridDim.z / 2;
     constexpr bool CROSS = MODE != MODE_ENC;              // Q from the packed query buffer, K/V through a per-session map
     static_assert(!(CROSS && X3), "the split-operand variant serves the encoder only");
     using AL = AttLayout<X3>;
@@ -194,11 +196,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ C
         constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(BQ, BKV, 0, 0);   // A=Q K-major, B=K K-major
         constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(BQ, DH, 0, 1);    // A=P (TMEM), B=V MN-major
         ptx::mbar_wait(bar_q, 0);
-        for (int j = 0; j < NT; ++j) {
-            const uint32_t s = j & 1, ph = (j >> 1) & 1;
-            ptx::mbar_wait(bar_kv_full + 8 * s, ph);
-            ptx::mbar_wait(bar_s_free, (j & 1) ^ 1);          // softmax threads have read S of tile j-1
-            ptx::tc_fence_after();
+        // Issue order: S_{j+1} = Q K_{j+1}^T goes to the tensor pipe BEFORE P_j V_j.  Both become issuable at the same
+        // moment (the softmax warps arrive on s_free and p_full together), and the softmax of tile j+1 only needs S_{j+1}:
+        // with P V first it sat behind ~750 clk of P V issue plus ~550 clk of barrier round trips per tile (measured with
+        // tools/attn_trace.py: tile period 3 950 clk, of which the exponentials are 2 050).  P and O are single-buffered,
+        // so the softmax warps wait for P_j V_j (bar_o_full) before their first write of tile j+1.
+        auto issue_s = [&](int j) {
+            const uint32_t s = j & 1;
+            if (tr && lane == 0) trace[j * 8 + 0] = clock64();
             if (lane == 0) {
                 const uint64_t dq = ptx::umma_desc_kmajor_sw128(sbase + SM_Q);
                 const uint64_t dk = ptx::umma_desc_kmajor_sw128(sbase + SM_K + s * NP * TILE_BYTES);
@@ -215,8 +220,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ C
                 ptx::umma_commit(bar_s_full);
             }
             __syncwarp();
-            ptx::mbar_wait(bar_p_full, j & 1);                // P of tile j is in TMEM, O_{j-1} was consumed
+        };
+        ptx::mbar_wait(bar_kv_full, 0);
+        ptx::tc_fence_after();
+        issue_s(0);
+        for (int j = 0; j < NT; ++j) {
+            const uint32_t s = j & 1;
+            if (j + 1 < NT) {
+                ptx::mbar_wait(bar_kv_full + 8 * ((j + 1) & 1), ((j + 1) >> 1) & 1);
+                if (tr && lane == 0) trace[(j + 1) * 8 + 5] = clock64();
+                ptx::mbar_wait(bar_s_free, j & 1);            // the softmax threads have read S of tile j
+                ptx::tc_fence_after();
+                issue_s(j + 1);
+            }
+            ptx::mbar_wait(bar_p_full, j & 1);                // P of tile j is in TMEM
             ptx::tc_fence_after();
+            if (tr && lane == 0) trace[j * 8 + 1] = clock64();
             if (lane == 0) {
                 const uint64_t dv = ptx::umma_desc_mnmajor_sw128(sbase + SM_V + s * NP * TILE_BYTES, BKV * 128);
                 const uint64_t dvl = ptx::umma_desc_mnmajor_sw128(sbase + SM_V + (s * NP + 1) * TILE_BYTES, BKV * 128);
@@ -232,6 +251,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ C
                 ptx::umma_commit(bar_kv_empty + 8 * s);
             }
             __syncwarp();
+            if (tr && lane == 0) trace[j * 8 + 7] = clock64();
         }
     } else {
         // ---- softmax: two threads per query row (warps w and w+4 share a TMEM lane quadrant; each owns 64 of
@@ -274,7 +294,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ C
             const int n_valid = MODE == MODE_SELF ? (pos0 + r + 1) - j * BKV - half * (BKV / 2)
                                                   : N_CTX - j * BKV - half * (BKV / 2);
             ptx::mbar_wait(bar_s_full, j & 1);
-            ptx::tc_fence_after();                            // (Q K^T of tile j retired => P V of tile j-1 did too)
+            if (j > 0) ptx::mbar_wait(bar_o_full, (j - 1) & 1);   // P_{j-1} V_{j-1} has read P and updated O (it was issued after
+            ptx::tc_fence_after();                            // Q K_j^T: see the issue order in the MMA warp)
+            if (tr && lane == 0 && warp == 2) trace[j * 8 + 2] = clock64();
             uint32_t va[16], vb[16];
             if (j == 0) {                                     // first tile: a true row maximum seeds the reference
                 float mx = -INFINITY;
@@ -331,6 +353,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ C
                 emit(va, 2);
                 ptx::tmem_ld_wait();
                 emit(vb, 3);
+                if (tr && lane == 0 && warp == 2) trace[j * 8 + 3] = clock64();
                 const float mx2 = fmaxf(mx, exchange(mx)) * LOG2E;    // the whole row's maximum in this tile
                 const bool need = mx2 > m + 8.0f;
                 if (!__any_sync(0xffffffffu, need)) { l += rs; break; }   // both warps of the row decide alike
@@ -351,6 +374,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ C
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_s_free);     // S fully consumed: next Q K^T may overwrite it
             ptx::mbar_arrive(bar_p_full);     // P written, O rescaled if needed: P V may run
+            if (tr && lane == 0 && (warp == 2 || warp == 9)) trace[j * 8 + (warp == 2 ? 4 : 6)] = clock64();
         };
         if (MODE == MODE_SELF) {
 #pragma unroll 1
@@ -396,7 +420,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ C
 
 }  // namespace
 
-void enc_attention_tcgen05(const void* qkv, int batch, int n_head, int d_model, void* out, cudaStream_t st, int num_sms) {
+void enc_attention_tcgen05(const void* qkv, int batch, int n_head, int d_model, void* out, cudaStream_t st, int num_sms,
+                           long long* trace_dev) {
     (void)num_sms;
     CUtensorMap tm;
     std::string err;
@@ -406,7 +431,7 @@ void enc_attention_tcgen05(const void* qkv, int batch, int n_head, int d_model, 
     if (first_on_device(seen))
         CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<MODE_ENC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AttLayout<false>::SMEM));
     dim3 grid((N_CTX + BQ - 1) / BQ, n_head, batch);
-    attn_tc_kernel<MODE_ENC, false><<<grid, ATT_THREADS, AttLayout<false>::SMEM, st>>>(tm, tm, nullptr, nullptr, 0, nullptr, n_head, d_model, N_CTX, out);
+    attn_tc_kernel<MODE_ENC, false><<<grid, ATT_THREADS, AttLayout<false>::SMEM, st>>>(tm, tm, nullptr, nullptr, 0, nullptr, n_head, d_model, N_CTX, out, trace_dev);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -447,7 +472,8 @@ void dec_cross_attention_tcgen05(const void* q, int total_rows, const DecJob* jo
         CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<MODE_CROSS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AttLayout<false>::SMEM));
     dim3 grid((max_rows + BQ - 1) / BQ, n_head, n_jobs);
     CUDA_CHECK(launch_pdl(attn_tc_kernel<MODE_CROSS, false>, grid, dim3(ATT_THREADS), (size_t)AttLayout<false>::SMEM, st, tm, tm,
-                          reinterpret_cast<const CUtensorMap*>(kv_maps_dev), jobs, layer, align_rank, n_head, d_model, N_CTX, out));
+                          reinterpret_cast<const CUtensorMap*>(kv_maps_dev), jobs, layer, align_rank, n_head, d_model, N_CTX, out,
+                          (long long*)nullptr));
 }
 
 // tensor map over one session's self-K/V cache viewed as [L * 2 * H * n_text_ctx rows, 64] bf16
@@ -472,7 +498,7 @@ void dec_self_attention_tcgen05(const void* q, int total_rows, const DecJob* job
     dim3 grid((max_rows + BQ - 1) / BQ, n_head, n_jobs);
     CUDA_CHECK(launch_pdl(attn_tc_kernel<MODE_SELF, false>, grid, dim3(ATT_THREADS), (size_t)AttLayout<false>::SMEM, st, tm, tm,
                           reinterpret_cast<const CUtensorMap*>(kv_maps_dev), jobs, layer, (const int32_t*)nullptr, n_head, d_model,
-                          n_text_ctx, out));
+                          n_text_ctx, out, (long long*)nullptr));
 }
 
 }  // namespace wlk

@@ -1811,6 +1811,20 @@ int wlk_op_encoder_attention(wlk_engine* e, int backend, const void* qkv, int ty
     WLK_API_END
 }
 
+int wlk_op_encoder_attention_trace(wlk_engine* e, const void* qkv, int batch, void* out, int64_t* stamps_host /*[12][8]*/) {
+    WLK_API_BEGIN
+    LOCK(e);
+    WLK_CHECK(qkv && out && stamps_host, "null argument");
+    long long* dev = nullptr;
+    CUDA_CHECK(cudaMalloc(&dev, 96 * 8));
+    CUDA_CHECK(cudaMemsetAsync(dev, 0, 96 * 8, e->st));
+    enc_attention_tcgen05(qkv, batch, e->dims.n_audio_head, e->dims.n_audio_state, out, e->st, e->num_sms, dev);
+    CUDA_CHECK(cudaMemcpyAsync(stamps_host, dev, 96 * 8, cudaMemcpyDeviceToHost, e->st));
+    CUDA_CHECK(cudaStreamSynchronize(e->st));
+    cudaFree(dev);
+    WLK_API_END
+}
+
 int wlk_op_median_filter(wlk_engine* e, const float* x_dev, float* out_dev, int rows, int cols, int width) {
     WLK_API_BEGIN
     LOCK(e);
