@@ -344,7 +344,7 @@ def seam_probe_threads(eng, B, n_ticks, warm_ticks, rng, context_tokens=300):
 
 
 def seam_search(eng, B0, Bmax, world, rng, n_ticks, warm_ticks, mode="cohort"):
-    """Probe B0, then walk up (pass) or down (fail) in steps of 16: at most three probes.  All ranks probe the same B
+    """Probe B0, then walk up (pass) or down (fail) in steps of 8: at most four probes.  All ranks probe the same B
     at the same time and a probe passes only if it passes on every rank."""
     import torch
     import torch.distributed as dist
@@ -362,10 +362,10 @@ def seam_search(eng, B0, Bmax, world, rng, n_ticks, warm_ticks, mode="cohort"):
         return r
 
     probes = [probe(B0)]
-    step = 16
+    step = 8
     if probes[0]["ok_all_ranks"]:
         B = B0
-        while len(probes) < 3 and B + step <= Bmax:
+        while len(probes) < 4 and B + step <= Bmax:
             r = probe(B + step)
             probes.append(r)
             if not r["ok_all_ranks"]:
@@ -373,7 +373,7 @@ def seam_search(eng, B0, Bmax, world, rng, n_ticks, warm_ticks, mode="cohort"):
             B += step
     else:
         B = B0
-        while len(probes) < 3 and B - step >= step:
+        while len(probes) < 4 and B - step >= step:
             B -= step
             r = probe(B)
             probes.append(r)

@@ -10,7 +10,7 @@ from whisperlivekit_b200.engine import WhisperEngine
 M, N, K = (int(x) for x in sys.argv[1:4]) if len(sys.argv) >= 4 else (24000, 5120, 1280)
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 out_bf16 = os.environ.get("OUT", "bf16") == "bf16"
-gelu = os.environ.get("GELU", "1") == "1"
+gelu = int(os.environ.get("GELU", "1"))        # bit 0: GELU, bit 1: fp32 residual accumulated in place (OUT=f32)
 eng = WhisperEngine(DIMS["micro"], None, [(0, 0)], precision="bf16", max_sessions=1, max_batch=1)
 A = torch.randn(M, K, device="cuda").bfloat16()
 ROT = int(os.environ.get("ROTATE", "1"))          # > 1: cycle through that many weight copies (HBM-streaming regime)

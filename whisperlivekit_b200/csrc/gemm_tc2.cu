@@ -89,7 +89,7 @@ template <bool X3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmWlo, int M, int N, int K,
-                Epilogue epi) {
+                Epilogue epi, int band_arg) {
     constexpr int NST = X3 ? STAGES2_X3 : STAGES2;
     constexpr uint32_t STAGE_TX = (X3 ? 4u : 2u) * (A_BYTES2 + B_BYTES2);       // bytes landing on a full barrier (both CTAs)
     extern __shared__ uint8_t smem_raw[];
@@ -113,8 +113,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int num_m = (M + BM2 - 1) / BM2, num_n = (N + BN2 - 1) / BN2;
     const int num_tiles = num_m * num_n;
     const int num_k = (K + BK2 - 1) / BK2;
-    // two n-blocks of a band in flight at a time; the band's A rows (256 x K bf16 each) should stay L2-resident
-    const int band = max(1, min(num_clusters / 2, (int)((48u << 20) / (512u * (uint32_t)K))));
+    // Rasterisation.  band_arg >= 1 (host heuristic): tiles run n-fastest inside bands of that many m-blocks.  When the
+    // whole weight matrix is L2-resident (every GEMM of a layer: <= 13 MB) the band is ONE m-block: the clusters that
+    // run concurrently take all n-blocks of the same few m-blocks and stream the same A slabs at the same time, so each A
+    // row block comes from HBM once (ncu, fc2 at 96 streams: 4.4 GB read for a 1.5 GB operand with 19-block bands).
+    // 0: two n-blocks of a band in flight at a time; the band's A rows (256 x K bf16 each) should stay L2-resident
+    const int band = band_arg >= 1 ? band_arg
+                                   : max(1, min(num_clusters / 2, (int)((48u << 20) / (512u * (uint32_t)K))));
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
@@ -240,7 +245,10 @@ static void launch_pair(const GemmArgs& g, const void* A_hi, const void* A_lo, c
     const int num_tiles = ((g.M + BM2 - 1) / BM2) * ((g.N + BN2 - 1) / BN2);
     int clusters = num_sms / 2;
     if (num_tiles < clusters) clusters = num_tiles;
-    gemm_tc2_kernel<X3><<<2 * clusters, NUM_THREADS2, SMEM2, st>>>(tmA, tmW, tmAlo, tmWlo, g.M, g.N, g.K, g.epi);
+    static const int forced_band = [] { const char* v = getenv("WLK_GEMM_BAND"); return v ? atoi(v) : -1; }();
+    const double w_bytes = (double)g.N * g.K * 2.0 * (X3 ? 2 : 1);
+    int band = forced_band >= 0 ? forced_band : (w_bytes <= 24.0 * (1 << 20) ? 1 : 0);
+    gemm_tc2_kernel<X3><<<2 * clusters, NUM_THREADS2, SMEM2, st>>>(tmA, tmW, tmAlo, tmWlo, g.M, g.N, g.K, g.epi, band);
     CUDA_CHECK(cudaGetLastError());
 }
 
