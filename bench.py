@@ -21,6 +21,8 @@ Numbers in the one JSON line:
   roofline    encoder GEMM class: algorithmic FLOPs / CUDA-event time inside the timed run vs the measured peak.
   exact_mode  the same scripted tick in WLK_PREC_BF16X3 (1e-3-on-logits mode): the price of exactness.
   other_configs  BASELINE configs 2, 3, 4 (per-GPU share: 64 streams + Sortformer), 5 in brief (each also the main line with --config).
+  incremental_mode  the LABELLED APPROXIMATE incremental encoder: streams per GPU and agreement with the parity mode (also --config
+              alignatt-large-v3-incremental as the main line).
   cpu_baseline / --impl reference: the STAGED UNMODIFIED reference (oracle/_ref: vendored torch Whisper behind its own
               AlignAtt hooks) on the host cores, same per-chunk workload (oracle/ref_driver.py).
 
@@ -50,7 +52,7 @@ PREFIX = int(os.environ.get("WLK_BENCH_PREFIX", "48"))            # the headline
 STEPS_PER_CHUNK = int(os.environ.get("WLK_BENCH_STEPS", "8"))
 UNIT = "concurrent real-time streams (audio-s per wall-s)"
 CONFIGS = ["alignatt-large-v3", "alignatt-base-en-1stream", "localagreement-large-v3-64", "alignatt-large-v3-sortformer-64",
-           "qwen-tower-128"]
+           "qwen-tower-128", "alignatt-large-v3-incremental"]
 
 
 def load_peaks():
@@ -697,7 +699,7 @@ def main():
         return
 
     # ---------------------------------------------------------------- side configs as the main line
-    if args.config != "alignatt-large-v3":
+    if args.config not in ("alignatt-large-v3", "alignatt-large-v3-incremental"):
         import torch
         torch.cuda.set_device(local_rank)
         sharded = args.config == "alignatt-large-v3-sortformer-64" and world > 1      # config 4: every rank carries 64 streams
@@ -860,6 +862,31 @@ def main():
         if rank == 0:
             print(f"[bench] {msg}", file=sys.stderr, flush=True)
 
+    if args.config == "alignatt-large-v3-incremental":
+        # the LABELLED APPROXIMATE mode as the main line (every rank carries B streams; max over ranks)
+        eng = make_engine("bf16", B + 16, B + 16)
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        inc = incremental_leg(eng, scripted, B, world, rng, base)
+        clocks = sampler.summary() if sampler else None
+        eng.close()
+        if rank == 0:
+            print(json.dumps(dict(metric=metric + "_incremental_encoder_approximate", value=inc["value"], unit=UNIT, n_gpus=world, steps=6,
+                                  warmup=3, ms_per_step=inc["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
+                                  dtype="bf16", data="synthetic (seeded random weights at true large-v3 dims, synthetic speech-like audio)",
+                                  config=dict(workload=workload.replace("fully re-encoded per chunk", "incremental encoder (approximate): "
+                                              "~27 of 1500 positions encoded per chunk"), model=args.model, streams_per_gpu=B,
+                                              parallelism=f"sessions sharded x{world}", approximate=True),
+                                  e2e=dict(value=inc["value"], unit=UNIT, h2d_bytes_per_step=B * world * CHUNK * 4,
+                                           d2h_bytes_per_step=B * world * 16 * (STEPS_PER_CHUNK + 1),
+                                           note="the timed tick takes one host chunk per stream (H2D) and returns per-token results (D2H)"),
+                                  clocks=clocks, detail=inc)))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
     eng = make_engine(args.precision, max(B, seam_bmax), max(B, seam_bmax))
     r = scripted(eng, B, args.steps, args.warmup)
     note(f"scripted tick: {r['ms_dev'] / args.steps:.1f} ms device-resident, {r['ms_io'] / args.steps:.1f} ms with host chunks")
@@ -901,7 +928,8 @@ def main():
                      value=Bx * world * CHUNK_S / (msx / 1e3), unit=UNIT, streams_per_gpu=Bx, ms_per_step=msx)
         if rank == 0 and world == 1:
             reuse = {"localagreement-large-v3-64": la64, "alignatt-large-v3-sortformer-64": diar64}
-            others = {c: (reuse[c] if reuse.get(c) is not None else run_side_config(c, local_rank)) for c in CONFIGS[1:]}
+            others = {c: (reuse[c] if reuse.get(c) is not None else run_side_config(c, local_rank))
+                      for c in CONFIGS[1:] if c != "alignatt-large-v3-incremental"}      # that one is `incremental_mode` above
 
     if rank == 0:
         peaks = load_peaks()

@@ -370,9 +370,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ C
                 l *= alpha;
                 if (need) m = mx2;
             }
-            ptx::tmem_st_wait();
             ptx::tc_fence_before();
-            ptx::mbar_arrive(bar_s_free);     // S fully consumed: next Q K^T may overwrite it
+            ptx::mbar_arrive(bar_s_free);     // S fully consumed (every load has been waited for): the next Q K^T may overwrite
+            ptx::tmem_st_wait();              // it while this thread's P stores are still draining
+            ptx::tc_fence_before();
             ptx::mbar_arrive(bar_p_full);     // P written, O rescaled if needed: P V may run
             if (tr && lane == 0 && (warp == 2 || warp == 9)) trace[j * 8 + (warp == 2 ? 4 : 6)] = clock64();
         };
