@@ -125,6 +125,37 @@ def test_encoder_attention_tcgen05(eng, d, H, B):
     e2.close()
 
 
+def test_encoder_attention_tcgen05_moving_reference():
+    """The one-pass softmax keeps a reference maximum per row and only moves it (rescaling O and l in TMEM and redoing the
+    tile) when a key tile exceeds it by more than 2^8.  Random inputs almost never take that path: here the keys of later
+    tiles are scaled up so that most rows move their reference several times, at different tiles."""
+    from whisperlivekit_b200.dims import ModelDimensions
+    from whisperlivekit_b200.engine import WhisperEngine
+    d, H, B = 256, 4, 2
+    e2 = WhisperEngine(ModelDimensions(80, 1500, d, H, 1, 51864, 448, 64, 1, 1), None, [(0, 0)], precision="bf16",
+                       max_sessions=1, max_batch=1)
+    g = torch.Generator(device="cuda").manual_seed(77)
+    x = torch.randn(B, 1500, 3, H, 64, device="cuda", generator=g) * 0.7
+    ramp = torch.ones(1500, device="cuda")
+    ramp[400:] = 1.8; ramp[700:] = 2.6; ramp[1000:] = 3.5; ramp[1300:] = 4.5       # key norms grow tile by tile
+    x[:, :, 1] *= ramp[None, :, None, None]
+    x[1, :, 1, 1] *= torch.linspace(1.0, 0.2, 1500, device="cuda")[:, None]         # ... and one head where they shrink
+    qkv = x.reshape(B * 1500, 3 * d).bfloat16()
+    out = torch.full((B * 1500, d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    e2.op_encoder_attention("tcgen05", qkv.data_ptr(), 1, B, out.data_ptr())
+    e2.sync()
+    xf = qkv.float().view(B, 1500, 3, H, 64)
+    q, k, v = xf[:, :, 0].transpose(1, 2), xf[:, :, 1].transpose(1, 2), xf[:, :, 2].transpose(1, 2)
+    s = q @ k.transpose(-1, -2)
+    jump = (s[..., 1280:].amax(-1) - s[..., :128].amax(-1)) * 1.4427                # log2 units, last tile vs first
+    assert (jump > 8).float().mean().item() > 0.5                                   # the path under test is really taken
+    ref = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B * 1500, d)
+    assert not torch.isnan(out.float()).any()
+    assert (out.float() - ref).abs().max().item() < 3e-2
+    e2.close()
+
+
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 512, 256), (1500, 1280, 1280), (3000, 384, 240),
                                    (257, 300, 72), (24000, 1280, 1280), (4500, 5120, 1280)])
 def test_gemm_tcgen05_cta_pair(eng, M, N, K):

@@ -108,3 +108,59 @@ def test_two_rank_qwen_streams_are_sharded_without_data_exchange():
         mels = mel_stream(450, dims.n_mels, seed=100 + stream)
         want = np.concatenate([eng.forward_chunk([sid], [mels[a: a + 150]])[0] for a in range(0, 450, 150)], axis=0)
         np.testing.assert_allclose(np.asarray(res[stream], np.float32), want, atol=1e-6)
+
+
+def _diar_worker(rank, world, port, q):
+    """Config 4's diarization leg under N > 1: every rank serves its shard of the streams with its own Sortformer (weights
+    broadcast once as a flat blob), per-stream speaker caches never leave their rank, no exchange on the data path."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.sortformer_oracle import OracleDiarizer, SortformerOracle
+    from whisperlivekit_b200.sortformer_dims import SORTFORMER_DIMS, synthetic_sortformer_state_dict, synthetic_two_speaker_audio
+    dims = SORTFORMER_DIMS["micro"]
+    ref_sd = synthetic_sortformer_state_dict(dims, seed=6)
+    names = sorted(ref_sd)
+    sizes = [ref_sd[k].size for k in names]
+    blob = torch.zeros(sum(sizes), dtype=torch.float32)
+    if rank == 0:
+        blob.copy_(torch.from_numpy(np.concatenate([ref_sd[k].reshape(-1) for k in names])))
+    broadcast_blob(blob, src=0)
+    sd, off = {}, 0
+    for k, n in zip(names, sizes):
+        sd[k] = blob[off: off + n].numpy().reshape(ref_sd[k].shape).copy()
+        off += n
+    model = SortformerOracle(dims, sd)
+    out = {}
+    for stream in shard_streams(3, world)[rank]:
+        d = OracleDiarizer(model)
+        audio = synthetic_two_speaker_audio(4.0, seed=50 + stream)
+        for k in range(4):
+            d.step(audio[k * 16000:(k + 1) * 16000])
+        out[stream] = (d.total_preds.numpy().tolist(), d.st["spkcache_len"], d.st["fifo_len"])
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_two_rank_diarization_streams_are_sharded_without_data_exchange():
+    from oracle.sortformer_oracle import OracleDiarizer, SortformerOracle
+    from whisperlivekit_b200.sortformer_dims import SORTFORMER_DIMS, synthetic_sortformer_state_dict, synthetic_two_speaker_audio
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_diar_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(x for _, d in sorted(q.get(timeout=300) for _ in procs) for x in d.items())
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [0, 1, 2]
+    dims = SORTFORMER_DIMS["micro"]
+    model = SortformerOracle(dims, synthetic_sortformer_state_dict(dims, seed=6))
+    for stream in range(3):
+        d = OracleDiarizer(model)
+        audio = synthetic_two_speaker_audio(4.0, seed=50 + stream)
+        for k in range(4):
+            d.step(audio[k * 16000:(k + 1) * 16000])
+        preds, sl, fl = res[stream]
+        np.testing.assert_allclose(np.asarray(preds, np.float32), d.total_preds.numpy(), atol=1e-6)
+        assert (sl, fl) == (d.st["spkcache_len"], d.st["fifo_len"])
