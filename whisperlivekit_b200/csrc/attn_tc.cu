@@ -421,9 +421,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ C
 
 }  // namespace
 
+void enc_attention_tcgen05_two_tile(const void* qkv, int batch, int n_head, int d_model, void* out, cudaStream_t st);   // attn_tc2.cu
+
 void enc_attention_tcgen05(const void* qkv, int batch, int n_head, int d_model, void* out, cudaStream_t st, int num_sms,
                            long long* trace_dev) {
     (void)num_sms;
+    // the serving kernel is the two-query-tile CTA of attn_tc2.cu; WLK_ATTN2=0 (and the pipeline trace) keep this file's
+    // one-tile CTA, which also serves the decoder prefills and the split-operand mode
+    static const bool two_tile = [] { const char* v = getenv("WLK_ATTN2"); return !(v && v[0] == '0'); }();
+    if (two_tile && trace_dev == nullptr) { enc_attention_tcgen05_two_tile(qkv, batch, n_head, d_model, out, st); return; }
     CUtensorMap tm;
     std::string err;
     WLK_CHECK(make_tmap_bf16_2d(&tm, qkv, (uint64_t)batch * N_CTX, (uint64_t)3 * d_model, (uint64_t)3 * d_model, BQ, DH, &err),
