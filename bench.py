@@ -244,6 +244,8 @@ def seam_probe(eng, B, n_ticks, warm_ticks, rng, mode="cohort", context_tokens=3
     -> dict(ok, p50/p95/max latency, start lag, policy statistics)"""
     if mode == "threads":
         return seam_probe_threads(eng, B, n_ticks, warm_ticks, rng, context_tokens)
+    if mode == "continuous":
+        return seam_probe_continuous(eng, B, n_ticks, warm_ticks, rng, context_tokens)
     from whisperlivekit_b200.cohort import CohortRunner
     pols = _seam_policies(eng, eng, B, rng, context_tokens)
     runner = CohortRunner(eng, max_batch=eng.max_batch)
@@ -285,6 +287,73 @@ def seam_probe(eng, B, n_ticks, warm_ticks, rng, mode="cohort", context_tokens=3
     for p in pols:
         p.close()
     return _seam_summary(B, "cohort", n_ticks, warm_ticks, lat, lag, aborted, errors, stats, wall,
+                         dict(engine_calls=rs["calls"], mean_sessions_per_call=rs["sessions"] / max(1, rs["calls"]),
+                              cohorts=rs["cohorts"], mean_cohort=rs["cohort_sessions"] / max(1, rs["cohorts"])))
+
+
+ADMIT_WAIT_S = float(os.environ.get("WLK_ADMIT_WAIT_S", "0.06"))
+
+
+def seam_probe_continuous(eng, B, n_ticks, warm_ticks, rng, context_tokens=300):
+    """Same load as the cohort mode, scheduled with continuous batching (cohort.CohortRunner.admit / round): streams whose
+    chunk has arrived are admitted BETWEEN rounds, their encode / prefill is served next, and they then share the token-step
+    rounds of the streams already running, instead of waiting for the running cohort to finish all of its rounds."""
+    from whisperlivekit_b200.cohort import CohortRunner
+    pols = _seam_policies(eng, eng, B, rng, context_tokens)
+    runner = CohortRunner(eng, max_batch=eng.max_batch)
+    chunks = (0.05 * rng.standard_normal((8, CHUNK))).astype(np.float32)
+    phases = np.arange(B) / B * CHUNK_S
+    total = warm_ticks + n_ticks
+    lat = np.full((B, total), 10.0); lag = np.full((B, total), 10.0)
+    nxt = np.zeros(B, np.int64)
+    flying = np.zeros(B, bool)
+    started = np.zeros(B)
+    stats = dict(prefix=[], iters=[], stops={})
+    errors, aborted = [], False
+    t_start = time.perf_counter() + 0.2
+
+    def finish(i, tr, t1):
+        k = nxt[i]
+        arrival = t_start + phases[i] + k * CHUNK_S
+        lat[i, k] = t1 - arrival; lag[i, k] = started[i] - arrival
+        if k >= warm_ticks:
+            stats["prefix"].append(tr.prefix_len); stats["iters"].append(len(tr.step_tokens))
+            stats["stops"][tr.stop] = stats["stops"].get(tr.stop, 0) + 1
+        nxt[i] += 1; flying[i] = False
+
+    try:
+        while (nxt < total).any():
+            now = time.perf_counter()
+            arrival = t_start + phases + nxt * CHUNK_S
+            idle = (~flying) & (nxt < total)
+            due = np.nonzero(idle & (arrival <= now))[0]
+            # admission: an encoder batch of one or two streams wastes the tensor cores, so arrivals wait until the engine is
+            # idle, or enough of them have gathered, or the oldest has waited ADMIT_WAIT_S
+            if len(due) and runner.busy() and len(due) < max(4, B // 8) and float((now - arrival[due]).max()) < ADMIT_WAIT_S:
+                due = due[:0]
+            if len(due):
+                if (nxt[due] >= warm_ticks).any() and float((now - arrival[due]).max()) > 2.0:
+                    aborted = True
+                    break
+                for i in due:
+                    pols[i].insert_audio(chunks[(i + nxt[i]) % 8])
+                    started[i] = now; flying[i] = True
+                for i, tr in runner.admit_many([(int(i), pols[i]) for i in due]):
+                    finish(i, tr, time.perf_counter())
+            if runner.busy():
+                done = runner.round()
+                t1 = time.perf_counter()
+                for i, tr in done:
+                    finish(i, tr, t1)
+            elif not len(due):
+                time.sleep(max(0.0, float(arrival[idle].min() - now)))
+    except Exception as e:                                                   # noqa: BLE001
+        errors.append(repr(e))
+    wall = time.perf_counter() - t_start
+    rs = runner.stats
+    for p in pols:
+        p.close()
+    return _seam_summary(B, "continuous", n_ticks, warm_ticks, lat, lag, aborted, errors, stats, wall,
                          dict(engine_calls=rs["calls"], mean_sessions_per_call=rs["sessions"] / max(1, rs["calls"]),
                               cohorts=rs["cohorts"], mean_cohort=rs["cohort_sessions"] / max(1, rs["cohorts"])))
 
@@ -673,7 +742,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip exact_mode and other_configs")
     ap.add_argument("--no-seam", action="store_true", help="skip the real-time paced run through the seam")
     ap.add_argument("--seam-ticks", type=int, default=16)
-    ap.add_argument("--seam-mode", default="cohort", choices=["cohort", "threads"])
+    ap.add_argument("--seam-mode", default="continuous", choices=["continuous", "cohort", "threads"])
     ap.add_argument("--seam-streams", type=int, default=0, help="first stream count probed through the seam (default: 2/3 of --streams)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -960,8 +1029,10 @@ def main():
                        d2h_bytes_per_step=int(seam_best["streams"] * world * 16 * (seam_best["mean_decode_iterations"] + 1)),
                        how="largest probed B per GPU with p95(chunk arrival -> infer() returned) < 0.5 s and no backlog growth; B "
                            "StreamingAlignAtt policies fed host chunks at real time with staggered phases, " +
-                           ("advanced in cohorts by one scheduler thread (cohort.CohortRunner), one batched engine call per round"
-                            if args.seam_mode == "cohort" else "one OS thread per stream over batching.BatchingEngine"),
+                           {"continuous": "one scheduler thread, continuous batching over policy requests (cohort.CohortRunner.admit / round): "
+                                          "arrivals are admitted between rounds and share the running streams' token-step rounds",
+                            "cohort": "advanced in closed cohorts by one scheduler thread (cohort.CohortRunner.run), one batched engine call per round",
+                            "threads": "one OS thread per stream over batching.BatchingEngine"}[args.seam_mode],
                        best=seam_best, probes=[dict(streams=p["streams"], ok=p["ok_all_ranks"], p95_latency_s=p["p95_latency_s"],
                                                     start_lag_last_third_s=p["start_lag_last_third_s"]) for p in seam_probes],
                        scripted_with_io=scripted_io)

@@ -21,12 +21,13 @@ ticks = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 dims = DIMS["large-v3"]
 eng = WhisperEngine(dims, synthetic_state_dict(dims, seed=0), ALIGNMENT_HEADS["large-v3"], precision="bf16", max_sessions=B, max_batch=B)
 rng = np.random.default_rng(1)
-bench.seam_probe(eng, B, 2, 2, rng)                       # warm up (graphs, tensor maps)
+mode = sys.argv[3] if len(sys.argv) > 3 else "continuous"
+bench.seam_probe(eng, B, 2, 2, rng, mode=mode)            # warm up (graphs, tensor maps)
 pr = cProfile.Profile()
 pr.enable()
-r = bench.seam_probe(eng, B, ticks, 4, rng)
+r = bench.seam_probe(eng, B, ticks, 4, rng, mode=mode)
 pr.disable()
-print({k: r[k] for k in ("streams", "ok", "p50_latency_s", "p95_latency_s", "wall_s", "engine_calls", "cohorts", "mean_cohort", "mean_decode_iterations")})
+print(mode, {k: r[k] for k in ("streams", "ok", "p50_latency_s", "p95_latency_s", "wall_s", "engine_calls", "cohorts", "mean_cohort", "mean_decode_iterations")})
 s = io.StringIO()
 pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(18)
 print(s.getvalue()[:4500])
