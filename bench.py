@@ -742,7 +742,9 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip exact_mode and other_configs")
     ap.add_argument("--no-seam", action="store_true", help="skip the real-time paced run through the seam")
     ap.add_argument("--seam-ticks", type=int, default=16)
-    ap.add_argument("--seam-mode", default="continuous", choices=["continuous", "cohort", "threads"])
+    ap.add_argument("--seam-mode", default="cohort", choices=["cohort", "continuous", "threads"],
+                    help="cohort: closed cohorts (best p95 capacity); continuous: arrivals join between rounds (measured: p50 0.20 s "
+                         "instead of 0.34 s at 64 streams, same p95, but the small encoder batches cost capacity: 80 streams run away)")
     ap.add_argument("--seam-streams", type=int, default=0, help="first stream count probed through the seam (default: 2/3 of --streams)")
     args = ap.parse_args()
     if args.warmup < 3:
