@@ -46,33 +46,34 @@ class AlignAttConfig:
     dry_penalty: bool = True
 
 
-def dry_penalties(seq: Sequence[int], eot: int) -> List[Tuple[int, float]]:
-    """DRY repetition penalty, host part (reference align_att_base.py:492-537).
-    Returns [(token, amount_to_subtract)]."""
-    seq = list(seq)
-    if len(seq) < 5:
+def dry_penalties(seq: Sequence[int], eot: int, max_run: int = 50) -> List[Tuple[int, float]]:
+    """DRY repetition penalty, host part -- the integer rule of the reference's ``_apply_dry_penalty``
+    (align_att_base.py:492-537), which must be reproduced exactly because it decides tokens: wherever the newest text
+    token occurred before, the token that FOLLOWED it then is penalised by 2^(run - 2), ``run`` being how many tokens the
+    two contexts share going backwards (special tokens end a run, at most ``max_run``; the longest run per follower wins;
+    runs of one are free).  -> [(token, amount_to_subtract)]"""
+    toks = list(seq)
+    tail = len(toks) - 1
+    if tail < 4 or toks[tail] >= eot:
         return []
-    last = seq[-1]
-    if last >= eot:
-        return []
-    penalties = {}
-    for i in range(len(seq) - 2, -1, -1):
-        if seq[i] != last:
-            continue
-        next_tok = seq[i + 1]
-        if next_tok >= eot:
-            continue
-        length = 1
-        while length < 50:
-            j, k = i - length, len(seq) - 1 - length
-            if j < 0 or k <= i:
+
+    def shared_run(i: int) -> int:
+        run = 1                                          # toks[i] == toks[tail] by construction
+        for back in range(1, max_run):
+            a, b = i - back, tail - back
+            if a < 0 or b <= i or toks[a] != toks[b] or toks[a] >= eot:
                 break
-            if seq[j] != seq[k] or seq[j] >= eot:
-                break
-            length += 1
-        if next_tok not in penalties or length > penalties[next_tok]:
-            penalties[next_tok] = length
-    return [(tok, 1.0 * 2.0 ** (length - 2)) for tok, length in penalties.items() if length >= 2]
+            run += 1
+        return run
+
+    longest: dict = {}
+    for i in reversed(range(tail)):                      # earlier occurrences, newest first (the reference's scan order)
+        if toks[i] != toks[tail] or toks[i + 1] >= eot:
+            continue
+        run = shared_run(i)
+        if run > longest.get(toks[i + 1], 0):
+            longest[toks[i + 1]] = run
+    return [(tok, 2.0 ** (run - 2)) for tok, run in longest.items() if run >= 2]
 
 
 def engine_select(eng, sids, suppress, first_ids, first_mask, biases, window_iters=16):
