@@ -613,7 +613,7 @@ def config_alignatt_sortformer(device=0, streams=64, seconds=4, eng=None):
                 sortformer_ms_per_step=float(np.mean(diar) * 1e3), streams=streams)
 
 
-def incremental_leg(eng, scripted, B, world, rng, base, pairs=8, ticks=10):
+def incremental_leg(eng, scripted, B, world, rng, base, pairs=8, ticks=10, seam_bmax=0):
     """The LABELLED APPROXIMATE incremental encoder (wlk_encode_incremental: encoder K/V retained, ~27 positions per chunk
     run through the encoder instead of 1500) next to the parity mode: (1) agreement -- `pairs` streams are held twice on the
     same engine, one session encoded in parity mode, one incrementally, same audio, same forced prefix, greedy steps
@@ -663,8 +663,20 @@ def incremental_leg(eng, scripted, B, world, rng, base, pairs=8, ticks=10):
         eng.close_session(s)
     was = eng.incremental_encoder
     eng.incremental_encoder = True
+    seam = None
     try:
         r = scripted(eng, B, 6, 3, profile_pass=False, io_only=True)
+        if seam_bmax and world == 1:
+            # the same real-time paced run through the policy seam as the headline's e2e, in this mode: two probes
+            p1 = seam_probe(eng, min(96, seam_bmax), 12, 6, rng, mode="cohort")
+            nxt = min(seam_bmax, 128) if p1["ok"] else 64
+            p2 = seam_probe(eng, nxt, 12, 6, rng, mode="cohort") if nxt != p1["streams"] else p1
+            ok = [p for p in (p1, p2) if p["ok"]]
+            seam = dict(value=max((p["streams"] for p in ok), default=0),
+                        probes=[dict(streams=p["streams"], ok=p["ok"], p50_latency_s=p["p50_latency_s"], p95_latency_s=p["p95_latency_s"],
+                                     mean_prefix_tokens=p["mean_prefix_tokens"]) for p in (p1, p2)],
+                        how="largest of two probed stream counts with p95(chunk arrival -> infer() returned) < 0.5 s, same policies, "
+                            "pacing and context-saturated prefixes as the headline's e2e")
     finally:
         eng.incremental_encoder = was
     ms = r["ms_io"] / 6
@@ -673,7 +685,7 @@ def incremental_leg(eng, scripted, B, world, rng, base, pairs=8, ticks=10):
                      "ring-addressed buffers, nothing moves when the 30 s window slides",
                 value=B * world * CHUNK_S / (ms / 1e3), unit=UNIT, streams_per_gpu=B, ms_per_step=ms,
                 note="sliding full 30 s window, one host chunk in per stream and tick (H2D inside), same decoder work as the headline tick",
-                encoder_rows_per_chunk=float(np.mean(rows)),
+                encoder_rows_per_chunk=float(np.mean(rows)), e2e_through_seam=seam,
                 agreement=dict(streams=pairs, ticks=ticks, compared=total, tokens_identical_pct=100.0 * tok_same / total,
                                frames_identical_pct=100.0 * frm_same / total, frames_within_2_pct=100.0 * frm_close / total,
                                max_abs_dlogits=float(np.max(dlog)), encoder_row_cosine_mean=float(np.mean(cos)),
@@ -969,7 +981,7 @@ def main():
     inc_mode = None
     if not args.no_extras and args.precision == "bf16":
         try:
-            inc_mode = incremental_leg(eng, scripted, B, world, rng, base)
+            inc_mode = incremental_leg(eng, scripted, B, world, rng, base, seam_bmax=seam_bmax)
             note(f"incremental encoder (approximate): {inc_mode['ms_per_step']:.1f} ms per tick at {B} streams/GPU, "
                  f"token agreement {inc_mode['agreement']['tokens_identical_pct']:.1f} %")
         except Exception as e:                                            # noqa: BLE001
