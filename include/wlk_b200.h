@@ -133,7 +133,8 @@ int wlk_decode(wlk_engine* e, const int32_t* sids, int n, const int32_t* tokens,
  * wlk_decode_all_logits: TextDecoder.forward returning the logits of EVERY fed position, as the word-timestamp
  *   pass needs (whisper/timing.py:197-201); logits_host = [n_tokens, n_vocab] fp32.
  * wlk_read_align_rows: softmax(qk) rows of the alignment heads accumulated in the current epoch,
- *   out = [n_align, rows, 1500] fp32 (what the cross-attention hooks of timing.py:186-192 capture).     */
+ *   out = [n_align, rows, 1500] fp32 (what the cross-attention hooks of timing.py:186-192 capture).      In the incremental encoder mode the 1500 columns of a row are
+ * ring slots, not frames: frame f is column (f + rot) mod 1500 (wlk_read_align_attn and the attended frames are in frame order). */
 int wlk_encode_mel(wlk_engine* e, int32_t sid, const float* mel_host, int32_t content_mel_len);
 int wlk_decode_all_logits(wlk_engine* e, int32_t sid, const int32_t* tokens, int n_tokens, int32_t sot_index,
                           float* logits_host);

@@ -178,3 +178,31 @@ def test_cif_fire_at_boundary_matches_reference(tmp_path):
         fired.append(f_r)
     # and through the whole infer(): the CIF decision only changes how many tokens are kept (align_att_base.py:296)
     assert isinstance(ours.infer(is_last=False), list)
+
+
+def test_nemo_checkpoint_reader_needs_no_nemo(tmp_path):
+    """plugin.sortformer_state_dict_from_nemo: a .nemo file is a tar holding model_weights.ckpt (a torch state_dict under NeMo's
+    parameter names); the reader returns numpy arrays and the engine-side loader skips the buffers of modules this path
+    replaces (checked on the GPU in tests/test_gpu_sortformer.py)."""
+    import io
+    import tarfile
+
+    import numpy as np
+    import torch
+
+    from whisperlivekit_b200 import plugin
+    from whisperlivekit_b200.sortformer_dims import SORTFORMER_DIMS, synthetic_sortformer_state_dict
+    d = SORTFORMER_DIMS["micro"]
+    sd = synthetic_sortformer_state_dict(d, 3)
+    blob = io.BytesIO()
+    torch.save({k: torch.from_numpy(v) for k, v in sd.items()}, blob)
+    path = tmp_path / "diar_streaming_sortformer_4spk-v2.nemo"
+    with tarfile.open(path, "w") as tar:
+        for name, data in (("./model_config.yaml", b"name: sortformer\n"), ("./model_weights.ckpt", blob.getvalue())):
+            info = tarfile.TarInfo(name)
+            info.size = len(data)
+            tar.addfile(info, io.BytesIO(data))
+    got = plugin.sortformer_state_dict_from_nemo(str(path))
+    assert sorted(got) == sorted(sd)
+    for k in sd:
+        assert got[k].dtype == np.float32 and np.array_equal(got[k], sd[k])
