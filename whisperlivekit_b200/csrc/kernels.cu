@@ -1126,22 +1126,6 @@ void inc_scatter_rows(const IncJob* jobs, int n, int max_rows, int d, const void
     else inc_scatter_rows_kernel<float><<<dim3(max_rows, n), 256, 0, st>>>(jobs, d, (const float*)src);
     CUDA_CHECK(cudaGetLastError());
 }
-template <typename T>
-__global__ void copy_plane_rows_kernel(T* __restrict__ dst, const T* __restrict__ src, int lo, int cnt) {
-    const int64_t plane = (int64_t)blockIdx.x * N_CTX * 64;
-    for (int i = threadIdx.x; i < cnt * 64; i += blockDim.x) {
-        int row = lo + i / 64;
-        if (row >= N_CTX) row -= N_CTX;
-        dst[plane + (int64_t)row * 64 + (i & 63)] = src[plane + (int64_t)row * 64 + (i & 63)];
-    }
-}
-void copy_plane_rows(void* dst, const void* src, int n_planes, int lo, int cnt, int type, cudaStream_t st) {
-    if (cnt <= 0) return;
-    if (type == DT_BF16) copy_plane_rows_kernel<bf16><<<n_planes, 256, 0, st>>>((bf16*)dst, (const bf16*)src, lo, cnt);
-    else copy_plane_rows_kernel<float><<<n_planes, 256, 0, st>>>((float*)dst, (const float*)src, lo, cnt);
-    CUDA_CHECK(cudaGetLastError());
-}
-
 // =====================================================================================
 // Word-timestamp kernels of the LocalAgreement path: native replacements of the reference's two Triton
 // kernels (whisper/triton_ops.py:13-103) with the semantics of its CPU path, which is the parity oracle

@@ -64,8 +64,6 @@ void inc_gather_conv1(const IncJob* jobs, int n, int max_rows1, int n_mels, void
 void inc_gather_conv2(const IncJob* jobs, int n, int max_rows, int d, const void* H1, void* A2, const float* enc_pos, float* posbuf,
                       int32_t* row_slot, int32_t* row_pos, int type, cudaStream_t st);
 void inc_scatter_rows(const IncJob* jobs, int n, int max_rows, int d, const void* src, int type, cudaStream_t st);
-// rows [lo, lo + cnt) (mod 1500) of every [1500][64] plane: dst plane <- src plane (template refresh of vacated slots)
-void copy_plane_rows(void* dst, const void* src, int n_planes, int lo, int cnt, int type, cudaStream_t st);
 
 void layernorm(const float* x, int64_t ldx, const float* w, const float* b, void* out, int out_type, int64_t ldo,
                int rows, int d, const int32_t* row_index_dev, cudaStream_t st);
