@@ -1067,8 +1067,9 @@ def main():
                         chunk_s=CHUNK_S, l2="working set (3.4 GB weights + per-stream KV) exceeds the 126 MB L2",
                         rtf_per_stream=(ms_dev / args.steps / 1e3) / CHUNK_S,
                         frac_of_encoder_gemm_stream_ceiling=value / world / (peaks["bf16_tflops"] / 5.18),
-                        parity="bf16 mode: tokens identical to the reference at 64/64 teacher-forced steps on two large-v3 streams, "
-                               "max |dlogits| 0.075 (tests/test_gpu_large_v3.py, profiles/r02_parity_large_v3_bf16.json)"),
+                        parity="bf16 mode: tokens identical to the reference wherever its top-2 logit gap exceeds the test's epsilon (63-64 of 64 "
+                               "teacher-forced steps on two large-v3 streams; the one flip seen has a reference gap of 0.006), max |dlogits| 0.05-0.075 "
+                               "(tests/test_gpu_large_v3.py, profiles/r02_parity_large_v3_bf16.json); fp32 and bf16x3 modes: 1e-3 on logits, identical"),
             e2e=e2e,
             gpu_launches=launches,
             clocks=r["clocks"],
